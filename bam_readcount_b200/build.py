@@ -1,0 +1,58 @@
+"""In-tree build of libbrc_engine.so for sm_100a (explicit nvcc; no JIT cache, no torch)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbrc_engine.so")
+SOURCES = ["brc_kernels.cu", "brc_engine.cu", "brc_format.cpp"]
+HEADERS = ["brc_device.cuh", "brc_engine_internal.h", os.path.join("..", "..", "include", "brc_engine.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--fmad=false",            # bit-exact float parity with the CPU reference: never contract a*b+c
+    "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden",
+    "-Xptxas", "-v",
+    "-shared",
+]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    for f in SOURCES + HEADERS:
+        if os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return os.path.getmtime(os.path.abspath(__file__)) > t
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-o", LIB] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or p.returncode != 0:
+        sys.stderr.write(p.stdout)
+    if p.returncode != 0:
+        raise RuntimeError("nvcc failed building libbrc_engine.so")
+    with open(os.path.join(HERE, "build.log"), "w") as fh:
+        fh.write(" ".join(cmd) + "\n" + p.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

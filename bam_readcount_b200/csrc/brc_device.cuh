@@ -1,0 +1,148 @@
+// brc_device.cuh — device-side data layout shared by the kernels and the host engine.
+//
+// HBM layout (all SoA unless noted):
+//   reads   : pos/flag/mapq/lib/l_qseq/nm/sm arrays + cigar/seq/qual byte pools with offsets
+//             (exactly the brc_read_batch of include/brc_engine.h, device pointers)
+//   desc    : ReadDesc[n_reads]  (AoS, 80 B, 16-B aligned) written by K0, read by K1 —
+//             the packed replacement of the reference's "Zm" string tag (R:auxfields.hpp:6-35)
+//   tiles   : TileInfo[n_tiles]  one per TILE consecutive computed sites of a region
+//   tile_lo / tile_hi : int32[n_tiles]  first / one-past-last read overlapping the tile (K0 atomics)
+//   results : per (row, slot) header + 13 primary accumulators, secondary key records
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace brc {
+
+constexpr int TILE = 128;            // sites per CTA of the pileup kernel (threads = sites)
+constexpr int N_STATS = 13;
+constexpr uint32_t LIB_NONE = 0xFFFFu;
+constexpr int KIND_INS = 6, KIND_DEL = 7;
+constexpr uint8_t NO_BASE = 255;
+
+// flag bits the reference filters on (R:bamreadcount.cpp:295-310)
+constexpr uint32_t FLAG_FILTER = 4u | 256u | 512u | 1024u;
+
+// ReadDesc.fm layout: flag[0:16) | mapq[16:24) | bits below
+constexpr uint32_t FM_SIMPLE = 1u << 24;     // CIGAR has exactly one ref-consuming op, of match type, and no I/D/N/P
+constexpr uint32_t FM_NM_ABSENT = 1u << 25;  // NM tag missing -> NM_TAG_MISSING warning per process_read
+constexpr uint32_t FM_SM_MISSING = 1u << 26; // proper pair without SM tag -> SM_TAG_MISSING warning per process_read
+
+struct __align__(16) ReadDesc {
+    // q0
+    int32_t pos;        // leftmost reference position
+    int32_t end;        // bam_endpos (== pos for reads the pileup buffer never admits)
+    int32_t l_qseq;
+    uint32_t fm;        // flag | mapq<<16 | FM_* bits
+    // q1 : the five values of fetch_func (R:bamreadcount.cpp:248-253)
+    int32_t mmq;        // sum_of_mismatch_qualities
+    int32_t clen;       // clipped_length
+    int32_t lclip;      // left_clip
+    int32_t tpi;        // three_prime_index
+    // q2
+    int32_t q2;         // q2_pos
+    float nmfrac;       // (float)NM / (float)clipped_length   (R:BasicStat.cpp:97), 0 if NM absent
+    int32_t se;         // contribution to sum_single_ended_map_qualities (R:BasicStat.cpp:78-91)
+    uint32_t lib_nc;    // lib[0:16) | min(n_cigar,0xFFFF)<<16
+    // q3
+    uint64_t seq_off;   // byte offset of this read's packed bases
+    uint64_t qual_off;  // byte offset of this read's qualities
+    // q4
+    int32_t qoff;       // SIMPLE reads: qpos = site - pos + qoff
+    uint32_t cigar_off; // index of first CIGAR op
+    uint32_t n_cigar;
+    uint32_t pad;
+};
+static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
+
+struct TileInfo {
+    int32_t pos0;       // absolute position of the tile's first site
+    int32_t n;          // sites in this tile (<= TILE)
+    int64_t slot0;      // result slot of the first site
+};
+
+struct RegionDev {
+    int32_t tid_slot;   // index into RefWin table
+    int32_t first_pos;  // max(beg-1, 0)
+    int32_t end;        // exclusive
+    int32_t ref_len_check; // site-list mode (R:bamreadcount.cpp:144-148)
+    int64_t tile_base;  // first tile of the region
+    int64_t read_lo, read_hi;
+};
+
+struct RefWin {
+    const char *seq;    // device pointer, seq[0] = position win_beg
+    int64_t chrom_len;
+    int64_t win_beg;
+    int64_t win_len;
+};
+
+struct ReadsDev {
+    int64_t n_reads;
+    const int32_t *pos;
+    const uint16_t *flag;
+    const uint8_t *mapq;
+    const uint16_t *lib;      // may be null
+    const int32_t *l_qseq;
+    const int32_t *nm;
+    const int32_t *sm;
+    const uint64_t *cigar_off;
+    const uint32_t *cigar;
+    const uint64_t *seq_off;
+    const uint8_t *seq;
+    const uint64_t *qual_off;
+    const uint8_t *qual;
+};
+
+struct ResultsDev {
+    int32_t n_rows;
+    int64_t n_slots;
+    uint32_t *ncover;     // [rows*slots]
+    uint32_t *npass;
+    uint8_t *flags;
+    uint8_t *pbase;
+    int32_t *sec_head;
+    uint32_t *pstats;     // [13][rows*slots]
+    // secondary key pool
+    int64_t sec_cap;
+    int32_t *sec_count;   // device counter (may exceed cap -> overflow)
+    int32_t *sec_next;
+    uint8_t *sec_kind;
+    int32_t *sec_len;
+    int64_t *sec_read;
+    int32_t *sec_qpos;
+    uint32_t *sec_stats;  // [13][sec_cap]
+    unsigned long long *warn; // [0]=SM missing events, [1]=NM missing events
+};
+
+struct PileupParams {
+    int32_t min_mapq, min_bq, per_lib, insertion_centric;
+    const ReadDesc *desc;
+    const uint32_t *cigar;
+    const uint8_t *seq;
+    const uint8_t *qual;
+    const TileInfo *tiles;
+    const int32_t *tile_lo;
+    const int32_t *tile_hi;
+    int64_t n_tiles;
+    ResultsDev res;
+};
+
+struct PrecomputeParams {
+    ReadsDev reads;
+    const RegionDev *regions;
+    int64_t n_regions;
+    const int32_t *region_of_read;  // null when n_regions == 1
+    const RefWin *refs;
+    ReadDesc *desc;
+    int32_t *tile_lo;
+    int32_t *tile_hi;
+};
+
+// launch wrappers (brc_kernels.cu)
+cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tiles, int32_t *sec_count,
+                              unsigned long long *warn, cudaStream_t s);
+cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s);
+cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s);
+
+}  // namespace brc

@@ -1,0 +1,490 @@
+// brc_engine.cu — host side of libbrc_engine.so: the C ABI of include/brc_engine.h.
+//
+// Mirrors the reference's region driver (R:src/exe/bam-readcount/bamreadcount.cpp:588-605,
+// 644-656): begin_region ≙ d.beg/d.end + bam_plbuf_init, push_read ≙ fetch_func +
+// bam_plbuf_push (admission rules of V:htslib-1.10/sam.c:4484-4531 evaluated here, on the
+// host, in file order), end_region ≙ bam_plbuf_push(0).  All arithmetic of the hot path runs
+// in the CUDA kernels of brc_kernels.cu; this file only batches, copies and launches.
+#include <algorithm>
+#include <cstring>
+
+#include "brc_engine_internal.h"
+
+using namespace brc;
+
+namespace brc {
+int set_error(brc_engine *e, int status, const std::string &msg) { if (e) e->err = msg; return status; }
+int set_cuda_error(brc_engine *e, cudaError_t ce, const char *what) {
+    if (e) e->err = std::string(what) + ": " + cudaGetErrorString(ce);
+    return BRC_E_CUDA;
+}
+const HostRef *find_ref(const brc_engine *e, int32_t tid) {
+    for (const auto &r : e->refs) if (r.tid == tid) return &r;
+    return nullptr;
+}
+}  // namespace brc
+
+#define CU(call, what) do { cudaError_t ce_ = (call); if (ce_ != cudaSuccess) return set_cuda_error(e, ce_, what); } while (0)
+
+extern "C" {
+
+int brc_abi_version(void) { return BRC_ABI_VERSION; }
+
+const char *brc_strerror(int s) {
+    switch (s) {
+    case BRC_OK: return "ok";
+    case BRC_E_INVALID: return "invalid argument or call order";
+    case BRC_E_NO_DEVICE: return "no usable CUDA device";
+    case BRC_E_CUDA: return "CUDA failure";
+    case BRC_E_NOMEM: return "out of memory";
+    case BRC_E_UNSORTED: return "reads not sorted by position";
+    case BRC_E_NO_REFERENCE: return "reference window missing or too small";
+    case BRC_E_BAD_LIBRARY: return "library id out of range";
+    case BRC_E_OVERFLOW: return "internal pool overflow";
+    default: return "unknown status";
+    }
+}
+
+const char *brc_last_error(const brc_engine *e) { return e ? e->err.c_str() : ""; }
+
+int brc_create(const brc_config *cfg, brc_engine **out) {
+    if (!cfg || !out) return BRC_E_INVALID;
+    *out = nullptr;
+    if (cfg->per_lib && (cfg->n_libs < 0 || cfg->n_libs > 65534)) return BRC_E_INVALID;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) { cudaGetLastError(); return BRC_E_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= n_dev) return BRC_E_NO_DEVICE;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { cudaGetLastError(); return BRC_E_NO_DEVICE; }
+    brc_engine *e = new (std::nothrow) brc_engine();
+    if (!e) return BRC_E_NOMEM;
+    e->cfg = *cfg;
+    e->n_rows = cfg->per_lib ? std::max(1, cfg->n_libs) : 1;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return BRC_E_CUDA; }
+    for (auto &ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) { delete e; return BRC_E_CUDA; }
+    *out = e;
+    return BRC_OK;
+}
+
+void brc_destroy(brc_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto &r : e->refs) r.dev.release();
+    DevBuf *bufs[] = {&e->d_refs, &e->d_desc, &e->d_tiles, &e->d_tile_lo, &e->d_tile_hi, &e->d_regions, &e->d_region_of_read,
+                      &e->d_ncover, &e->d_npass, &e->d_flags, &e->d_pbase, &e->d_sec_head, &e->d_pstats, &e->d_sec_count,
+                      &e->d_sec_next, &e->d_sec_kind, &e->d_sec_len, &e->d_sec_read, &e->d_sec_qpos, &e->d_sec_stats, &e->d_warn};
+    for (auto *b : bufs) b->release();
+    for (auto &b : e->d_in) b.release();
+    PinBuf *pins[] = {&e->h_ncover, &e->h_npass, &e->h_flags, &e->h_pbase, &e->h_sec_head, &e->h_pstats, &e->h_sec_next,
+                      &e->h_sec_kind, &e->h_sec_len, &e->h_sec_read, &e->h_sec_qpos, &e->h_sec_stats, &e->h_misc};
+    for (auto *b : pins) b->release();
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64_t chrom_len, int64_t win_beg,
+                      const char *seq, int64_t win_len) {
+    if (!e || !seq || win_len < 0 || win_beg < 0 || chrom_len < 0) return BRC_E_INVALID;
+    cudaSetDevice(e->cfg.device);
+    HostRef *r = nullptr;
+    for (auto &x : e->refs) if (x.tid == tid) r = &x;
+    if (!r) { e->refs.emplace_back(); r = &e->refs.back(); }
+    r->tid = tid; r->name = contig_name ? contig_name : ""; r->chrom_len = chrom_len; r->win_beg = win_beg; r->win_len = win_len;
+    r->seq.assign(seq, (size_t)win_len);
+    CU(r->dev.reserve((size_t)win_len + 16), "cudaMalloc(reference)");
+    CU(cudaMemcpyAsync(r->dev.p, r->seq.data(), (size_t)win_len, cudaMemcpyHostToDevice, e->stream), "H2D reference");
+    CU(cudaStreamSynchronize(e->stream), "sync reference");
+    // refresh the device RefWin table
+    std::vector<RefWin> tab(e->refs.size());
+    for (size_t i = 0; i < e->refs.size(); ++i)
+        tab[i] = RefWin{e->refs[i].dev.as<char>(), e->refs[i].chrom_len, e->refs[i].win_beg, e->refs[i].win_len};
+    CU(e->d_refs.reserve(tab.size() * sizeof(RefWin)), "cudaMalloc(refs)");
+    CU(cudaMemcpy(e->d_refs.p, tab.data(), tab.size() * sizeof(RefWin), cudaMemcpyHostToDevice), "H2D refs");
+    return BRC_OK;
+}
+
+int brc_reset(brc_engine *e) {
+    if (!e) return BRC_E_INVALID;
+    e->reads.clear(); e->regions.clear(); e->region_open = false; e->adm.reset(); e->n_indel_ops = 0;
+    e->results_valid = false; e->planned = false; e->tiles.clear(); e->regions_dev.clear(); e->n_slots = 0;
+    for (auto &w : e->warn_counts) w = 0;
+    return BRC_OK;
+}
+
+int brc_begin_region(brc_engine *e, int32_t tid, int32_t beg, int32_t end, int32_t site_list_mode) {
+    if (!e || e->region_open) return set_error(e, BRC_E_INVALID, "begin_region: previous region still open");
+    brc_region r{};
+    r.tid = tid; r.beg = beg; r.end = end; r.site_list_mode = site_list_mode;
+    r.read_lo = r.read_hi = e->reads.n();
+    r.first_pos = beg - 1 > 0 ? beg - 1 : 0;
+    r.slot_base = e->regions.empty() ? 0 : e->regions.back().slot_base + e->regions.back().n_slots;
+    r.n_slots = 0;
+    e->regions.push_back(r);
+    e->region_open = true; e->adm.reset(); e->open_max_end = r.first_pos;
+    e->results_valid = false; e->planned = false;
+    return BRC_OK;
+}
+
+static inline int64_t cigar_rlen(const uint32_t *cig, uint32_t n, int64_t *n_indel) {
+    int64_t l = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t op = cig[k] & 0xF;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) l += cig[k] >> 4;
+        if (op == 1 || op == 2) ++*n_indel;
+    }
+    return l;
+}
+
+int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_t mapq, uint16_t lib, int32_t l_qseq,
+                  int32_t nm, int32_t sm, uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq,
+                  const uint8_t *qual) {
+    if (!e || !e->region_open) return set_error(e, BRC_E_INVALID, "push_read: no open region");
+    if (l_qseq < 0 || (n_cigar && !cigar) || (l_qseq && (!seq || !qual))) return set_error(e, BRC_E_INVALID, "push_read: null data");
+    brc_region &rg = e->regions.back();
+    Admission &A = e->adm;
+    // fetch_func runs for every yielded record but has no observable effect for records the
+    // pileup buffer refuses; bam_plp_push (V:htslib-1.10/sam.c:4484-4531):
+    if (tid < 0 || (flag & 4)) return BRC_OK;                                   // :4488-4490
+    if (e->cfg.per_lib && lib != BRC_LIB_NONE && (int)lib >= e->n_rows) return set_error(e, BRC_E_BAD_LIBRARY, "push_read: library id >= n_libs");
+    int64_t indel_ops = 0;
+    const int64_t end = n_cigar > 0 ? (int64_t)pos + cigar_rlen(cigar, n_cigar, &indel_ops) : (int64_t)pos + 1;  // bam_endpos
+    if (A.it_tid == tid && A.it_pos == pos) {                                   // :4491 maxcnt rule
+        while (!A.live_ends.empty() && A.live_ends.top() < A.it_pos) A.live_ends.pop();   // retired while draining positions < it_pos
+        if ((int64_t)A.live_ends.size() + 1 > (int64_t)e->cfg.max_cnt) return BRC_OK;
+    }
+    if (tid < A.max_tid || (tid == A.max_tid && pos < A.max_pos)) return set_error(e, BRC_E_UNSORTED, "push_read: reads out of order");
+    A.max_tid = tid; A.max_pos = pos;
+    const bool linked = end > A.it_pos || tid > A.it_tid;                       // :4513
+    if (tid > A.it_tid) { A.live_ends = decltype(A.live_ends)(); }
+    A.it_tid = tid; A.it_pos = pos;                                             // the drain leaves the iterator at max_pos
+    if (!linked) return BRC_OK;
+    A.live_ends.push(end);
+    if (tid != rg.tid) return BRC_OK;   // another contig's read can never span a site of this region
+
+    HostReads &H = e->reads;
+    H.pos.push_back(pos); H.flag.push_back(flag); H.mapq.push_back(mapq); H.lib.push_back(lib); H.l_qseq.push_back(l_qseq);
+    H.nm.push_back(nm); H.sm.push_back(sm); H.region.push_back((int32_t)(e->regions.size() - 1));
+    H.cigar.insert(H.cigar.end(), cigar, cigar + n_cigar); H.cigar_off.push_back(H.cigar.size());
+    const size_t sb = (size_t)(l_qseq + 1) / 2;
+    H.seq.insert(H.seq.end(), seq, seq + sb); H.seq_off.push_back(H.seq.size());
+    H.qual.insert(H.qual.end(), qual, qual + l_qseq); H.qual_off.push_back(H.qual.size());
+    e->n_indel_ops += indel_ops;
+    if (end > e->open_max_end) e->open_max_end = end;
+    rg.read_hi = H.n();
+    return BRC_OK;
+}
+
+int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
+    if (!e || !b) return BRC_E_INVALID;
+    if (!e->region_open) return set_error(e, BRC_E_INVALID, "push_reads: no open region");
+    const int32_t rtid = e->regions.back().tid;
+    for (int64_t i = 0; i < b->n_reads; ++i) {
+        const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
+        int rc = brc_push_read(e, b->tid ? b->tid[i] : rtid, b->pos[i], b->flag[i], b->mapq[i], b->lib ? b->lib[i] : (uint16_t)0,
+                               b->l_qseq[i], b->nm[i], b->sm[i], (uint32_t)(c1 - c0), b->cigar + c0, b->seq + b->seq_off[i],
+                               b->qual + b->qual_off[i]);
+        if (rc != BRC_OK) return rc;
+    }
+    return BRC_OK;
+}
+
+int brc_end_region(brc_engine *e) {
+    if (!e || !e->region_open) return set_error(e, BRC_E_INVALID, "end_region: no open region");
+    brc_region &rg = e->regions.back();
+    // sites are only ever produced where an admitted read spans them: clamp the dense slot range
+    int64_t last = std::min<int64_t>(rg.end, e->open_max_end);
+    rg.n_slots = (int32_t)std::max<int64_t>(0, last - rg.first_pos);
+    e->region_open = false;
+    return BRC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// geometry + launches
+// ---------------------------------------------------------------------------------------------
+static int build_geometry(brc_engine *e, const brc_region *regs, int64_t n_regions) {
+    e->tiles.clear(); e->regions_dev.clear();
+    int64_t n_slots = 0;
+    for (int64_t g = 0; g < n_regions; ++g) {
+        const brc_region &r = regs[g];
+        int slot = -1;
+        for (size_t i = 0; i < e->refs.size(); ++i) if (e->refs[i].tid == r.tid) slot = (int)i;
+        if (slot < 0) return set_error(e, BRC_E_NO_REFERENCE, "no reference set for region contig (the reference binary dereferences NULL here)");
+        RegionDev d{};
+        d.tid_slot = slot; d.first_pos = r.first_pos; d.end = r.first_pos + r.n_slots; d.ref_len_check = r.site_list_mode;
+        d.tile_base = (int64_t)e->tiles.size(); d.read_lo = r.read_lo; d.read_hi = r.read_hi;
+        e->regions_dev.push_back(d);
+        if (r.slot_base != n_slots) return set_error(e, BRC_E_INVALID, "regions: slot_base must be the running sum of n_slots");
+        for (int32_t o = 0; o < r.n_slots; o += TILE)
+            e->tiles.push_back(TileInfo{r.first_pos + o, std::min(TILE, r.n_slots - o), r.slot_base + o});
+        n_slots += r.n_slots;
+    }
+    e->n_slots = n_slots;
+    return BRC_OK;
+}
+
+static int alloc_outputs(brc_engine *e, int64_t n_reads_cap) {
+    const int64_t rs = (int64_t)e->n_rows * e->n_slots;
+    const int64_t rs1 = std::max<int64_t>(rs, 1);
+    CU(e->d_desc.reserve((size_t)std::max<int64_t>(n_reads_cap, 1) * sizeof(ReadDesc)), "cudaMalloc(desc)");
+    const size_t nt = std::max<size_t>(e->tiles.size(), 1);
+    CU(e->d_tiles.reserve(nt * sizeof(TileInfo)), "cudaMalloc(tiles)");
+    CU(e->d_tile_lo.reserve(nt * 4), "cudaMalloc(tile_lo)");
+    CU(e->d_tile_hi.reserve(nt * 4), "cudaMalloc(tile_hi)");
+    CU(e->d_regions.reserve(std::max<size_t>(e->regions_dev.size(), 1) * sizeof(RegionDev)), "cudaMalloc(regions)");
+    CU(e->d_ncover.reserve(rs1 * 4), "cudaMalloc(ncover)");
+    CU(e->d_npass.reserve(rs1 * 4), "cudaMalloc(npass)");
+    CU(e->d_flags.reserve(rs1), "cudaMalloc(flags)");
+    CU(e->d_pbase.reserve(rs1), "cudaMalloc(pbase)");
+    CU(e->d_sec_head.reserve(rs1 * 4), "cudaMalloc(sec_head)");
+    CU(e->d_pstats.reserve(rs1 * 4 * N_STATS), "cudaMalloc(pstats)");
+    CU(e->d_sec_count.reserve(16), "cudaMalloc(sec_count)");
+    CU(e->d_warn.reserve(32), "cudaMalloc(warn)");
+    return BRC_OK;
+}
+
+static int alloc_sec(brc_engine *e, int64_t cap) {
+    cap = std::max<int64_t>(cap, 1024);
+    e->sec_cap = cap;
+    CU(e->d_sec_next.reserve(cap * 4), "cudaMalloc(sec_next)");
+    CU(e->d_sec_kind.reserve(cap), "cudaMalloc(sec_kind)");
+    CU(e->d_sec_len.reserve(cap * 4), "cudaMalloc(sec_len)");
+    CU(e->d_sec_read.reserve(cap * 8), "cudaMalloc(sec_read)");
+    CU(e->d_sec_qpos.reserve(cap * 4), "cudaMalloc(sec_qpos)");
+    CU(e->d_sec_stats.reserve(cap * 4 * N_STATS), "cudaMalloc(sec_stats)");
+    return BRC_OK;
+}
+
+static ResultsDev results_dev(brc_engine *e) {
+    ResultsDev S{};
+    S.n_rows = e->n_rows; S.n_slots = e->n_slots;
+    S.ncover = e->d_ncover.as<uint32_t>(); S.npass = e->d_npass.as<uint32_t>(); S.flags = e->d_flags.as<uint8_t>();
+    S.pbase = e->d_pbase.as<uint8_t>(); S.sec_head = e->d_sec_head.as<int32_t>(); S.pstats = e->d_pstats.as<uint32_t>();
+    S.sec_cap = e->sec_cap; S.sec_count = e->d_sec_count.as<int32_t>(); S.sec_next = e->d_sec_next.as<int32_t>();
+    S.sec_kind = e->d_sec_kind.as<uint8_t>(); S.sec_len = e->d_sec_len.as<int32_t>(); S.sec_read = e->d_sec_read.as<int64_t>();
+    S.sec_qpos = e->d_sec_qpos.as<int32_t>(); S.sec_stats = e->d_sec_stats.as<uint32_t>();
+    S.warn = e->d_warn.as<unsigned long long>();
+    return S;
+}
+
+static int upload_geometry(brc_engine *e, cudaStream_t s) {
+    if (!e->tiles.empty())
+        CU(cudaMemcpyAsync(e->d_tiles.p, e->tiles.data(), e->tiles.size() * sizeof(TileInfo), cudaMemcpyHostToDevice, s), "H2D tiles");
+    if (!e->regions_dev.empty())
+        CU(cudaMemcpyAsync(e->d_regions.p, e->regions_dev.data(), e->regions_dev.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, s), "H2D regions");
+    return BRC_OK;
+}
+
+// K(init) + K0 + K1 on stream s.  Returns BRC_E_OVERFLOW (after syncing) if the secondary pool was too small.
+static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStream_t s, bool check_overflow) {
+    PrecomputeParams P0{};
+    P0.reads = e->dev_reads; P0.regions = e->d_regions.as<RegionDev>(); P0.n_regions = (int64_t)e->regions_dev.size();
+    P0.region_of_read = d_region_of_read; P0.refs = e->d_refs.as<RefWin>(); P0.desc = e->d_desc.as<ReadDesc>();
+    P0.tile_lo = e->d_tile_lo.as<int32_t>(); P0.tile_hi = e->d_tile_hi.as<int32_t>();
+    PileupParams P1{};
+    P1.min_mapq = e->cfg.min_mapq; P1.min_bq = e->cfg.min_bq; P1.per_lib = e->cfg.per_lib; P1.insertion_centric = e->cfg.insertion_centric;
+    P1.desc = e->d_desc.as<ReadDesc>(); P1.cigar = e->dev_reads.cigar; P1.seq = e->dev_reads.seq; P1.qual = e->dev_reads.qual;
+    P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size();
+    P1.res = results_dev(e);
+
+    e->launch_count = 0;
+    CU(cudaEventRecord(e->ev[0], s), "event");
+    CU(launch_init_tiles(P0.tile_lo, P0.tile_hi, P1.n_tiles, P1.res.sec_count, P1.res.warn, s), "launch init_tiles"); e->launch_count++;
+    CU(launch_precompute(P0, s), "launch read_precompute"); if (P0.reads.n_reads) e->launch_count++;
+    CU(cudaEventRecord(e->ev[1], s), "event");
+    CU(launch_pileup(P1, s), "launch pileup"); if (P1.n_tiles) e->launch_count++;
+    CU(cudaEventRecord(e->ev[2], s), "event");
+    if (check_overflow) {
+        int32_t cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, P1.res.sec_count, 4, cudaMemcpyDeviceToHost, s), "D2H sec_count");
+        CU(cudaStreamSynchronize(s), "sync kernels");
+        e->h_n_sec = cnt;
+        if ((int64_t)cnt > e->sec_cap) return BRC_E_OVERFLOW;
+    }
+    return BRC_OK;
+}
+
+static int fetch_results(brc_engine *e, cudaStream_t s) {
+    const int64_t rs = (int64_t)e->n_rows * e->n_slots;
+    int32_t cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost, s), "D2H sec_count");
+    CU(cudaStreamSynchronize(s), "sync");
+    if ((int64_t)cnt > e->sec_cap) return set_error(e, BRC_E_OVERFLOW, "secondary key pool overflow (re-plan with a larger n_sec_cap)");
+    e->h_n_sec = cnt;
+    const int64_t rs1 = std::max<int64_t>(rs, 1), ns1 = std::max<int64_t>(cnt, 1);
+    CU(e->h_ncover.reserve(rs1 * 4), "pin"); CU(e->h_npass.reserve(rs1 * 4), "pin"); CU(e->h_flags.reserve(rs1), "pin");
+    CU(e->h_pbase.reserve(rs1), "pin"); CU(e->h_sec_head.reserve(rs1 * 4), "pin"); CU(e->h_pstats.reserve(rs1 * 4 * N_STATS), "pin");
+    CU(e->h_sec_next.reserve(ns1 * 4), "pin"); CU(e->h_sec_kind.reserve(ns1), "pin"); CU(e->h_sec_len.reserve(ns1 * 4), "pin");
+    CU(e->h_sec_read.reserve(ns1 * 8), "pin"); CU(e->h_sec_qpos.reserve(ns1 * 4), "pin"); CU(e->h_sec_stats.reserve(ns1 * 4 * N_STATS), "pin");
+    CU(e->h_misc.reserve(64), "pin");
+    if (rs) {
+        CU(cudaMemcpyAsync(e->h_ncover.p, e->d_ncover.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_npass.p, e->d_npass.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, rs, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_pbase.p, e->d_pbase.p, rs, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_sec_head.p, e->d_sec_head.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_pstats.p, e->d_pstats.p, rs * 4 * N_STATS, cudaMemcpyDeviceToHost, s), "D2H");
+    }
+    if (cnt) {
+        CU(cudaMemcpyAsync(e->h_sec_next.p, e->d_sec_next.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_sec_kind.p, e->d_sec_kind.p, (size_t)cnt, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_sec_len.p, e->d_sec_len.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_sec_read.p, e->d_sec_read.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s), "D2H");
+        CU(cudaMemcpyAsync(e->h_sec_qpos.p, e->d_sec_qpos.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H");
+        // compact the [13][sec_cap] device layout to [13][cnt] on the host
+        CU(cudaMemcpy2DAsync(e->h_sec_stats.p, (size_t)cnt * 4, e->d_sec_stats.p, (size_t)e->sec_cap * 4, (size_t)cnt * 4, N_STATS,
+                             cudaMemcpyDeviceToHost, s), "D2H");
+    }
+    e->h_sec_cap = cnt;
+    CU(cudaMemcpyAsync(e->h_misc.p, e->d_warn.p, 16, cudaMemcpyDeviceToHost, s), "D2H warn");
+    CU(cudaStreamSynchronize(s), "sync D2H");
+    const unsigned long long *w = e->h_misc.as<unsigned long long>();
+    e->warn_counts[0] = (int64_t)w[0]; e->warn_counts[1] = (int64_t)w[1]; e->warn_counts[2] = 0;
+    // LIBRARY_UNAVAILABLE fires once per abandoned site callback (R:bamreadcount.cpp:281-284)
+    int64_t lu = 0;
+    if (e->cfg.per_lib) {
+        const uint8_t *fl = e->h_flags.as<uint8_t>();
+        for (int64_t sidx = 0; sidx < e->n_slots; ++sidx) {
+            bool ab = false;
+            for (int r = 0; r < e->n_rows && !ab; ++r) ab = (fl[(int64_t)r * e->n_slots + sidx] & 1) != 0;
+            lu += ab;
+        }
+    }
+    e->warn_counts[3] = lu;
+    e->results_valid = true;
+    return BRC_OK;
+}
+
+extern "C" {
+
+int brc_compute(brc_engine *e) {
+    if (!e || e->region_open) return set_error(e, BRC_E_INVALID, "compute: a region is still open");
+    cudaSetDevice(e->cfg.device);
+    int rc = build_geometry(e, e->regions.data(), (int64_t)e->regions.size());
+    if (rc != BRC_OK) return rc;
+    HostReads &H = e->reads;
+    const int64_t n = H.n();
+    // reference window must cover every read's span (K0 reads it; the emitter reads deletion alleles)
+    for (const brc_region &r : e->regions) {
+        const HostRef *hr = find_ref(e, r.tid);
+        if (!hr) return set_error(e, BRC_E_NO_REFERENCE, "no reference for contig");
+        if (r.read_hi > r.read_lo) {
+            int64_t lo = H.pos[(size_t)r.read_lo], hi = (int64_t)r.first_pos + r.n_slots;
+            lo = std::max<int64_t>(0, std::min<int64_t>(lo, r.first_pos));
+            hi = std::min(hi, hr->chrom_len);
+            if (lo < hr->win_beg || hi > hr->win_beg + hr->win_len)
+                return set_error(e, BRC_E_NO_REFERENCE, "reference window does not cover the region's reads");
+        }
+    }
+    rc = alloc_outputs(e, n);
+    if (rc != BRC_OK) return rc;
+    cudaStream_t s = e->stream;
+    // H2D of the read arrays
+    const void *src[14] = {H.pos.data(), H.flag.data(), H.mapq.data(), H.lib.data(), H.l_qseq.data(), H.nm.data(), H.sm.data(),
+                           H.cigar_off.data(), H.cigar.data(), H.seq_off.data(), H.seq.data(), H.qual_off.data(), H.qual.data(),
+                           H.region.data()};
+    const size_t bytes[14] = {(size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 2, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
+                              (size_t)(n + 1) * 8, H.cigar.size() * 4, (size_t)(n + 1) * 8, H.seq.size(), (size_t)(n + 1) * 8,
+                              H.qual.size(), (size_t)n * 4};
+    for (int k = 0; k < 14; ++k) {
+        CU(e->d_in[k].reserve(bytes[k] + 16), "cudaMalloc(reads)");
+        if (bytes[k]) CU(cudaMemcpyAsync(e->d_in[k].p, src[k], bytes[k], cudaMemcpyHostToDevice, s), "H2D reads");
+    }
+    ReadsDev &R = e->dev_reads;
+    R.n_reads = n; R.pos = e->d_in[0].as<int32_t>(); R.flag = e->d_in[1].as<uint16_t>(); R.mapq = e->d_in[2].as<uint8_t>();
+    R.lib = e->d_in[3].as<uint16_t>(); R.l_qseq = e->d_in[4].as<int32_t>(); R.nm = e->d_in[5].as<int32_t>(); R.sm = e->d_in[6].as<int32_t>();
+    R.cigar_off = e->d_in[7].as<uint64_t>(); R.cigar = e->d_in[8].as<uint32_t>(); R.seq_off = e->d_in[9].as<uint64_t>();
+    R.seq = e->d_in[10].as<uint8_t>(); R.qual_off = e->d_in[11].as<uint64_t>(); R.qual = e->d_in[12].as<uint8_t>();
+    rc = upload_geometry(e, s);
+    if (rc != BRC_OK) return rc;
+    int64_t cap = std::max<int64_t>(e->sec_cap, (int64_t)e->n_rows * e->n_slots / 8 + 2 * e->n_indel_ops + 1024);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        rc = alloc_sec(e, cap);
+        if (rc != BRC_OK) return rc;
+        rc = run_kernels(e, e->regions.size() > 1 ? e->d_in[13].as<int32_t>() : nullptr, s, true);
+        if (rc != BRC_E_OVERFLOW) break;
+        cap = std::max<int64_t>(cap * 2, e->h_n_sec + 1024);
+    }
+    if (rc != BRC_OK) return rc == BRC_E_OVERFLOW ? set_error(e, rc, "secondary key pool overflow") : rc;
+    return fetch_results(e, s);
+}
+
+int brc_get_results(brc_engine *e, brc_results *out) {
+    if (!e || !out) return BRC_E_INVALID;
+    if (!e->results_valid) return set_error(e, BRC_E_INVALID, "get_results: no results (call brc_compute)");
+    out->n_regions = (int64_t)e->regions.size(); out->regions = e->regions.data(); out->n_rows = e->n_rows; out->n_slots = e->n_slots;
+    out->ncover = e->h_ncover.as<uint32_t>(); out->npass = e->h_npass.as<uint32_t>(); out->flags = e->h_flags.as<uint8_t>();
+    out->pbase = e->h_pbase.as<uint8_t>(); out->sec_head = e->h_sec_head.as<int32_t>(); out->pstats = e->h_pstats.as<uint32_t>();
+    out->n_sec = e->h_n_sec; out->sec_next = e->h_sec_next.as<int32_t>(); out->sec_kind = e->h_sec_kind.as<uint8_t>();
+    out->sec_len = e->h_sec_len.as<int32_t>(); out->sec_read = e->h_sec_read.as<int64_t>(); out->sec_qpos = e->h_sec_qpos.as<int32_t>();
+    out->sec_stats = e->h_sec_stats.as<uint32_t>();
+    return BRC_OK;
+}
+
+int brc_get_warning_counts(brc_engine *e, int64_t out[4]) {
+    if (!e || !out) return BRC_E_INVALID;
+    for (int k = 0; k < 4; ++k) out[k] = e->warn_counts[k];
+    return BRC_OK;
+}
+
+int brc_plan_device(brc_engine *e, const brc_region *regions, int64_t n_regions, int64_t n_reads_cap, int64_t n_sec_cap) {
+    if (!e || !regions || n_regions <= 0) return BRC_E_INVALID;
+    cudaSetDevice(e->cfg.device);
+    e->regions.assign(regions, regions + n_regions);
+    e->region_open = false; e->results_valid = false;
+    int rc = build_geometry(e, e->regions.data(), n_regions);
+    if (rc != BRC_OK) return rc;
+    rc = alloc_outputs(e, n_reads_cap);
+    if (rc != BRC_OK) return rc;
+    rc = alloc_sec(e, n_sec_cap > 0 ? n_sec_cap : (int64_t)e->n_rows * e->n_slots / 4 + 4096);
+    if (rc != BRC_OK) return rc;
+    rc = upload_geometry(e, e->stream);
+    if (rc != BRC_OK) return rc;
+    CU(cudaStreamSynchronize(e->stream), "sync plan");
+    e->planned = true;
+    return BRC_OK;
+}
+
+int brc_run_device(brc_engine *e, const brc_read_batch *b, const int32_t *dev_region_of_read, void *stream) {
+    if (!e || !b) return BRC_E_INVALID;
+    if (!e->planned) return set_error(e, BRC_E_INVALID, "run_device: call brc_plan_device first");
+    if (e->regions.size() > 1 && !dev_region_of_read) return set_error(e, BRC_E_INVALID, "run_device: region_of_read required for >1 region");
+    cudaSetDevice(e->cfg.device);
+    ReadsDev &R = e->dev_reads;
+    R.n_reads = b->n_reads; R.pos = b->pos; R.flag = b->flag; R.mapq = b->mapq; R.lib = b->lib; R.l_qseq = b->l_qseq; R.nm = b->nm; R.sm = b->sm;
+    R.cigar_off = b->cigar_off; R.cigar = b->cigar; R.seq_off = b->seq_off; R.seq = b->seq; R.qual_off = b->qual_off; R.qual = b->qual;
+    if ((size_t)std::max<int64_t>(b->n_reads, 1) * sizeof(ReadDesc) > e->d_desc.cap) return set_error(e, BRC_E_INVALID, "run_device: batch larger than planned n_reads_cap");
+    e->results_valid = false;
+    return run_kernels(e, dev_region_of_read, (cudaStream_t)stream, false);
+}
+
+int brc_device_results(brc_engine *e, brc_results *out) {
+    if (!e || !out || !e->planned) return BRC_E_INVALID;
+    out->n_regions = (int64_t)e->regions.size(); out->regions = e->regions.data(); out->n_rows = e->n_rows; out->n_slots = e->n_slots;
+    out->ncover = e->d_ncover.as<uint32_t>(); out->npass = e->d_npass.as<uint32_t>(); out->flags = e->d_flags.as<uint8_t>();
+    out->pbase = e->d_pbase.as<uint8_t>(); out->sec_head = e->d_sec_head.as<int32_t>(); out->pstats = e->d_pstats.as<uint32_t>();
+    out->n_sec = e->sec_cap; out->sec_next = e->d_sec_next.as<int32_t>(); out->sec_kind = e->d_sec_kind.as<uint8_t>();
+    out->sec_len = e->d_sec_len.as<int32_t>(); out->sec_read = e->d_sec_read.as<int64_t>(); out->sec_qpos = e->d_sec_qpos.as<int32_t>();
+    out->sec_stats = e->d_sec_stats.as<uint32_t>();
+    return BRC_OK;
+}
+
+int brc_fetch_device_results(brc_engine *e, void *stream) {
+    if (!e || !e->planned) return BRC_E_INVALID;
+    cudaSetDevice(e->cfg.device);
+    return fetch_results(e, (cudaStream_t)stream);
+}
+
+int brc_last_launch_count(const brc_engine *e) { return e ? e->launch_count : 0; }
+float brc_last_stage_ms(const brc_engine *e, int stage) {
+    if (!e || stage < 0 || stage > 2) return 0.0f;
+    // events were recorded on the launching stream around K0 and K1; wait for the last one
+    if (cudaEventSynchronize(e->ev[2]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e->ev[stage == 2 ? 0 : stage], e->ev[stage == 2 ? 2 : stage + 1]) != cudaSuccess) { cudaGetLastError(); return 0.0f; }
+    return ms;
+}
+
+}  // extern "C"

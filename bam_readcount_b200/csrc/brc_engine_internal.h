@@ -1,0 +1,122 @@
+// brc_engine_internal.h — host-side engine state shared by brc_engine.cu and brc_format.cpp.
+#pragma once
+#include <cstdint>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/brc_engine.h"
+#include "brc_device.cuh"
+
+namespace brc {
+
+struct DevBuf {   // grow-only device allocation
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct PinBuf {   // grow-only pinned host allocation
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostRef {
+    int32_t tid = -1;
+    std::string name;
+    int64_t chrom_len = 0, win_beg = 0, win_len = 0;
+    std::string seq;       // host copy (deletion alleles, reference base column)
+    DevBuf dev;            // device copy
+};
+
+struct HostReads {         // staging SoA of admitted reads, all regions, file order
+    std::vector<int32_t> pos, l_qseq, nm, sm, region;
+    std::vector<uint16_t> flag, lib;
+    std::vector<uint8_t> mapq;
+    std::vector<uint64_t> cigar_off{0}, seq_off{0}, qual_off{0};
+    std::vector<uint32_t> cigar;
+    std::vector<uint8_t> seq, qual;
+    int64_t n() const { return (int64_t)pos.size(); }
+    void clear() {
+        pos.clear(); l_qseq.clear(); nm.clear(); sm.clear(); region.clear(); flag.clear(); lib.clear(); mapq.clear();
+        cigar_off.assign(1, 0); seq_off.assign(1, 0); qual_off.assign(1, 0); cigar.clear(); seq.clear(); qual.clear();
+    }
+};
+
+// pileup-buffer admission state of the open region (bam_plp_push, V:htslib-1.10/sam.c:4484-4531)
+struct Admission {
+    int32_t it_tid = 0; int64_t it_pos = 0;        // iterator position (calloc'd to 0, V:sam.c:4154)
+    int32_t max_tid = -1; int64_t max_pos = -1;
+    std::priority_queue<int64_t, std::vector<int64_t>, std::greater<int64_t>> live_ends;
+    void reset() { it_tid = 0; it_pos = 0; max_tid = -1; max_pos = -1; live_ends = decltype(live_ends)(); }
+};
+
+}  // namespace brc
+
+struct brc_engine {
+    brc_config cfg{};
+    int n_rows = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    std::vector<brc::HostRef> refs;
+    brc::DevBuf d_refs;              // RefWin table
+
+    // push path
+    brc::HostReads reads;
+    std::vector<brc_region> regions;
+    bool region_open = false;
+    brc::Admission adm;
+    int64_t open_max_end = 0;
+    int64_t n_indel_ops = 0;
+
+    // geometry (push path or plan_device)
+    std::vector<brc::TileInfo> tiles;
+    std::vector<brc::RegionDev> regions_dev;
+    int64_t n_slots = 0;
+    int64_t sec_cap = 0;
+    bool planned = false;
+
+    // device buffers
+    brc::DevBuf d_in[14];            // uploaded read arrays (push path)
+    brc::DevBuf d_desc, d_tiles, d_tile_lo, d_tile_hi, d_regions, d_region_of_read;
+    brc::DevBuf d_ncover, d_npass, d_flags, d_pbase, d_sec_head, d_pstats;
+    brc::DevBuf d_sec_count, d_sec_next, d_sec_kind, d_sec_len, d_sec_read, d_sec_qpos, d_sec_stats, d_warn;
+    brc::ReadsDev dev_reads{};       // what the kernels read (push path: d_in; device path: caller's pointers)
+
+    // host results (pinned)
+    brc::PinBuf h_ncover, h_npass, h_flags, h_pbase, h_sec_head, h_pstats;
+    brc::PinBuf h_sec_next, h_sec_kind, h_sec_len, h_sec_read, h_sec_qpos, h_sec_stats, h_misc;
+    int64_t h_n_sec = 0;
+    int64_t h_sec_cap = 0;           // stride of h_sec_stats
+    bool results_valid = false;
+    int64_t warn_counts[4] = {0, 0, 0, 0};
+
+    int launch_count = 0;
+    float stage_ms[3] = {0, 0, 0};
+};
+
+namespace brc {
+int set_error(brc_engine *e, int status, const std::string &msg);
+int set_cuda_error(brc_engine *e, cudaError_t ce, const char *what);
+const HostRef *find_ref(const brc_engine *e, int32_t tid);
+}  // namespace brc

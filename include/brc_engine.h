@@ -1,0 +1,220 @@
+/*
+ * brc_engine.h — C ABI of the B200-native pileup-readcount engine (libbrc_engine.so).
+ *
+ * Drop-in boundary for ONE path of genome/bam-readcount: the two htslib callbacks its
+ * region loops register:
+ *
+ *   typedef int (*bam_fetch_f)(const bam1_t *b, void *data);                 V:bam.h:452
+ *       fetch_func()      R:src/exe/bam-readcount/bamreadcount.cpp:114-261
+ *   typedef int (*bam_pileup_f)(uint32_t tid, uint32_t pos, int n,
+ *                               const bam_pileup1_t *pl, void *data);        V:bam.h:388
+ *       pileup_func()     R:src/exe/bam-readcount/bamreadcount.cpp:265-419
+ *
+ * plus the per-region driver around them (bam_plbuf_init / samfetch / bam_plbuf_push(0) /
+ * bam_plbuf_destroy, R:bamreadcount.cpp:591-605 and :650-656).  Mapping:
+ *
+ *   reference call (file:line)                               engine entry point
+ *   -------------------------------------------------------  ---------------------------
+ *   pileup_data_t d{} + flags          R:...:430-465          brc_create(&cfg,&e)
+ *   load_reference()/fai_fetch         R:...:83-90            brc_set_reference()
+ *   d.beg/d.end + bam_plbuf_init +
+ *     bam_plp_set_maxcnt               R:...:588-592,644-651  brc_begin_region()
+ *   fetch_func(b) + bam_plbuf_push(b)  R:...:114-261,259      brc_push_read() / brc_push_reads()
+ *   bam_plbuf_push(0,buf)+destroy      R:...:603-604,655-656  brc_end_region()
+ *   every pileup_func() invocation     R:...:265-419          brc_compute() -> brc_get_results()
+ *   operator<<(BasicStat) + cout line  R:BasicStat.cpp:110-159,
+ *                                      R:...:351-416          brc_format_text()
+ *   ReadWarnings counters              R:ReadWarnings.hpp     brc_get_warning_counts()
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary; nothing throws.
+ * All functions return 0 (BRC_OK) or a negative brc_status.  One caller thread per handle
+ * (the reference's callbacks are not re-entrant either, SURVEY.md §8b "Threading").
+ * The library REQUIRES a CUDA device: there is no CPU fallback (brc_create fails with
+ * BRC_E_NO_DEVICE when none is usable).
+ */
+#ifndef BRC_ENGINE_H
+#define BRC_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BRC_API __attribute__((visibility("default")))
+#else
+#define BRC_API
+#endif
+
+typedef enum {
+    BRC_OK = 0,
+    BRC_E_INVALID = -1,       /* bad argument / call order */
+    BRC_E_NO_DEVICE = -2,     /* no usable CUDA device */
+    BRC_E_CUDA = -3,          /* CUDA runtime failure (brc_last_error has the text) */
+    BRC_E_NOMEM = -4,
+    BRC_E_UNSORTED = -5,      /* reads of a region not sorted by position (htslib: "Pileup aborts", V:htslib-1.10/sam.c:4502-4511) */
+    BRC_E_NO_REFERENCE = -6,  /* reference window does not cover the region (the reference binary would SIGSEGV) */
+    BRC_E_BAD_LIBRARY = -7,   /* library id >= n_libs */
+    BRC_E_OVERFLOW = -8       /* internal pool overflow that retry could not resolve */
+} brc_status;
+
+#define BRC_TAG_ABSENT INT32_MIN  /* NM:i / SM:i tag not present on the read */
+#define BRC_LIB_NONE 0xFFFFu      /* read has no RG, or its @RG has no LB (bam_get_library()==NULL, V:bam.c:77-101) */
+
+/* allele kinds of a result key */
+#define BRC_KIND_INS 6            /* kinds 0..5 index "=ACGTN" (R:bamreadcount.cpp:34) */
+#define BRC_KIND_DEL 7
+#define BRC_NO_BASE 255
+
+/* the 13 accumulators of BasicStat (R:src/lib/bamrc/BasicStat.hpp:12-24), in print order */
+enum {
+    BRC_S_COUNT = 0,      /* read_count                      u32 */
+    BRC_S_MAPQ = 1,       /* sum_map_qualities               u32 */
+    BRC_S_BASEQ = 2,      /* sum_base_qualities              u32 (not accumulated for indel keys) */
+    BRC_S_SE_MAPQ = 3,    /* sum_single_ended_map_qualities  u32 */
+    BRC_S_PLUS = 4,       /* num_plus_strand                 u32 */
+    BRC_S_MINUS = 5,      /* num_minus_strand                u32 */
+    BRC_S_POS_FRAC = 6,   /* sum_event_location              f32 bits */
+    BRC_S_NM_FRAC = 7,    /* sum_number_of_mismatches        f32 bits */
+    BRC_S_MMQS = 8,       /* sum_of_mismatch_qualities       u32 */
+    BRC_S_NQ2 = 9,        /* num_q2_reads                    u32 */
+    BRC_S_Q2_DIST = 10,   /* sum_q2_distance                 f32 bits */
+    BRC_S_CLIP_LEN = 11,  /* sum_of_clipped_lengths          u32 */
+    BRC_S_3P_DIST = 12,   /* sum_3p_distance                 f32 bits */
+    BRC_N_STATS = 13
+};
+
+typedef struct brc_engine brc_engine;
+
+/* pileup_data_t's option fields (R:bamreadcount.cpp:55-71, flags :438-446) */
+typedef struct {
+    int32_t min_mapq;           /* -q */
+    int32_t min_bq;             /* -b */
+    int32_t max_cnt;            /* -d  (bam_plp_set_maxcnt) */
+    int32_t per_lib;            /* -p */
+    int32_t insertion_centric;  /* -i */
+    int32_t n_libs;             /* number of distinct LB names; ids are ranks in byte-lexicographic (std::map) order */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t reserved;
+} brc_config;
+
+/* Struct-of-arrays batch of decoded reads in file order == the bam1_t fields the path reads
+ * (SURVEY.md §8a row a1).  Host pointers for brc_push_reads, device pointers for brc_run_device. */
+typedef struct {
+    int64_t n_reads;
+    const int32_t *tid;         /* may be NULL (= region tid) ; reads with tid<0 are not admitted (V:sam.c:4488) */
+    const int32_t *pos;         /* bam1_core_t.pos, 0-based */
+    const uint16_t *flag;       /* bam1_core_t.flag */
+    const uint8_t *mapq;        /* bam1_core_t.qual */
+    const uint16_t *lib;        /* library id or BRC_LIB_NONE; may be NULL when !per_lib */
+    const int32_t *l_qseq;      /* bam1_core_t.l_qseq */
+    const int32_t *nm;          /* bam_aux2i(NM) or BRC_TAG_ABSENT */
+    const int32_t *sm;          /* bam_aux2i(SM) or BRC_TAG_ABSENT */
+    const uint64_t *cigar_off;  /* [n_reads+1] offsets into cigar */
+    const uint32_t *cigar;      /* bam1_cigar(b): len<<4|op */
+    const uint64_t *seq_off;    /* [n_reads+1] byte offsets into seq */
+    const uint8_t *seq;         /* bam1_seq(b): 4-bit packed, (l_qseq+1)/2 bytes per read */
+    const uint64_t *qual_off;   /* [n_reads+1] byte offsets into qual */
+    const uint8_t *qual;        /* bam1_qual(b) */
+} brc_read_batch;
+
+/* One region of the reference's loops: compute sites [beg-1, end), print [beg, end). */
+typedef struct {
+    int32_t tid;
+    int32_t beg;                /* d.beg : 0-based first printed site */
+    int32_t end;                /* d.end : exclusive */
+    int32_t site_list_mode;     /* 1: -l loop (ref_len check R:...:144-148, queues cleared per region :605); 0: argv regions */
+    int64_t read_lo, read_hi;   /* this region's reads inside the pushed stream */
+    int64_t slot_base;          /* first result slot; slot = slot_base + (pos - (beg-1 clamped to >=0)) */
+    int32_t first_pos;          /* max(beg-1,0) */
+    int32_t n_slots;            /* end - first_pos */
+} brc_region;
+
+/* Result arrays (engine-owned, valid until the next brc_compute/brc_reset/brc_destroy).
+ * Dense "slots": one per computed site per library row (row 0 = "all" when !per_lib);
+ * index = row * n_slots + slot.  Every slot carries its PRIMARY key (the first passing base
+ * class seen at the site) inline; further keys (other bases, indel alleles) are chained
+ * through `sec_*` records starting at sec_head. */
+typedef struct {
+    int64_t n_regions;
+    const brc_region *regions;
+    int32_t n_rows;
+    int64_t n_slots;
+    const uint32_t *ncover;     /* reads spanning the site (before any filter) == pileup n for that library */
+    const uint32_t *npass;      /* events passing mapq/baseq/flag filters (this row's share of mapq_n, R:...:312) */
+    const uint8_t *flags;       /* bit0: a read without library spans the site (-p abandons it, R:...:281-284) */
+    const uint8_t *pbase;       /* primary base class 0..5 or BRC_NO_BASE */
+    const int32_t *sec_head;    /* first secondary record or -1 */
+    const uint32_t *pstats;     /* [BRC_N_STATS][n_rows*n_slots] primary accumulators (floats as IEEE bits) */
+    int64_t n_sec;
+    const int32_t *sec_next;    /* next record of the same (row,slot) or -1 */
+    const uint8_t *sec_kind;    /* 0..5 base class, BRC_KIND_INS, BRC_KIND_DEL */
+    const int32_t *sec_len;     /* indel length (0 for bases) */
+    const int64_t *sec_read;    /* representative read (index into the pushed stream) carrying the insertion bases */
+    const int32_t *sec_qpos;    /* its qpos: inserted bases are read bases qpos+1 .. qpos+len */
+    const uint32_t *sec_stats;  /* [BRC_N_STATS][n_sec] */
+} brc_results;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+BRC_API int brc_abi_version(void);
+BRC_API int brc_create(const brc_config *cfg, brc_engine **out);
+BRC_API void brc_destroy(brc_engine *e);
+BRC_API const char *brc_last_error(const brc_engine *e);   /* text of the last failure on this handle ("" if none) */
+BRC_API const char *brc_strerror(int status);
+
+/* ---- reference window (load_reference, R:bamreadcount.cpp:83-90) ------------------------
+ * seq[0] is position win_beg of contig tid; chrom_len is the full contig length (d.len).
+ * The window must cover every base the region's reads and deletion alleles touch. */
+BRC_API int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64_t chrom_len, int64_t win_beg,
+                      const char *seq, int64_t win_len);
+
+/* ---- region loop ----------------------------------------------------------------------- */
+BRC_API int brc_reset(brc_engine *e);                      /* drop all pushed regions/reads and results */
+BRC_API int brc_begin_region(brc_engine *e, int32_t tid, int32_t beg, int32_t end, int32_t site_list_mode);
+/* one record, in file order: fetch_func(b) + bam_plbuf_push(b).  lib: id or BRC_LIB_NONE. */
+BRC_API int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_t mapq, uint16_t lib, int32_t l_qseq,
+                  int32_t nm, int32_t sm, uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq,
+                  const uint8_t *qual);
+BRC_API int brc_push_reads(brc_engine *e, const brc_read_batch *batch);   /* bulk form of brc_push_read */
+BRC_API int brc_end_region(brc_engine *e);
+
+/* Runs the GPU path over everything pushed since brc_reset: H2D, per-read precompute kernel,
+ * pileup/accumulate kernel, D2H.  Reads not admitted by the pileup buffer (tid<0, FUNMAP,
+ * the -d rule of V:htslib-1.10/sam.c:4491) are dropped on the host while batching. */
+BRC_API int brc_compute(brc_engine *e);
+BRC_API int brc_get_results(brc_engine *e, brc_results *out);
+/* counts of the reference's per-event warnings: [0]=SM_TAG_MISSING [1]=NM_TAG_MISSING
+ * [2]=Zm_TAG_MISSING (always 0) [3]=LIBRARY_UNAVAILABLE (R:src/lib/bamrc/ReadWarnings.hpp:12-18) */
+BRC_API int brc_get_warning_counts(brc_engine *e, int64_t out[4]);
+
+/* Text of the reference's STDOUT for region `region_index` (all regions if -1), formatted
+ * exactly as R:bamreadcount.cpp:351-416 + R:BasicStat.cpp:110-159.  lib_names: n_libs strings.
+ * Returns the number of bytes required (excluding NUL); writes at most cap-1 bytes + NUL. */
+BRC_API int64_t brc_format_text(brc_engine *e, int64_t region_index, const char *const *lib_names, char *buf, int64_t cap);
+
+/* ---- device-resident path (bench "value": inputs already in HBM) -------------------------
+ * brc_plan_device: fix the region geometry (host array of n_regions regions with read_lo/hi,
+ * slot_base, first_pos, n_slots filled) and size the outputs.  brc_run_device: launch the
+ * kernels on `stream` (a cudaStream_t) over a batch whose pointers are DEVICE pointers and the
+ * reference window set by brc_set_reference; results stay on the device.  brc_device_results
+ * returns device pointers in a brc_results.  brc_fetch_device_results copies them to the host
+ * arrays brc_get_results exposes. */
+BRC_API int brc_plan_device(brc_engine *e, const brc_region *regions, int64_t n_regions, int64_t n_reads_cap,
+                    int64_t n_sec_cap);
+BRC_API int brc_run_device(brc_engine *e, const brc_read_batch *dev_batch, const int32_t *dev_region_of_read, void *stream);
+BRC_API int brc_device_results(brc_engine *e, brc_results *out);
+BRC_API int brc_fetch_device_results(brc_engine *e, void *stream);
+/* kernels launched by the last brc_run_device/brc_compute (for bench.py's gpu_launches) */
+BRC_API int brc_last_launch_count(const brc_engine *e);
+/* elapsed GPU milliseconds of the named stage of the last run, measured with CUDA events on the
+ * launching stream: 0 = per-read precompute kernel, 1 = pileup kernel, 2 = whole device step */
+BRC_API float brc_last_stage_ms(const brc_engine *e, int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRC_ENGINE_H */

@@ -1,0 +1,42 @@
+"""GPU: the CUDA engine, called through the C ABI (libbrc_engine.so), against
+  (1) the reference's golden files and the committed reference-binary outputs — text, byte-exact;
+  (2) the CPU oracle on the same inputs — every raw accumulator of every computed site,
+      bit-exact (integers AND the float32 sums: accumulation order is preserved);
+  (3) the reference's warning counters.
+"""
+import pytest
+
+import cases
+import golden_jobs
+
+pytestmark = pytest.mark.gpu
+
+JOBS = golden_jobs.jobs()
+
+
+def _first_diff(a: str, b: str) -> str:
+    la, lb = a.splitlines(), b.splitlines()
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            return f"line {i}:\n got: {x[:400]}\nwant: {y[:400]}"
+    return f"length differs: got {len(la)} lines, want {len(lb)}"
+
+
+@pytest.mark.parametrize("job", JOBS, ids=[j[0] for j in JOBS])
+def test_engine_text_matches_reference_golden(job):
+    _, getter, flags, site_list, golden = job
+    case = getter()
+    text, _, _, _ = cases.run_engine(case, flags, site_list=site_list, want_dump=False)
+    want = cases.load_golden_text(golden)
+    assert text == want, _first_diff(text, want)
+
+
+@pytest.mark.parametrize("job", JOBS, ids=[j[0] for j in JOBS])
+def test_engine_accumulators_match_oracle_bit_exact(job):
+    _, getter, flags, _, _ = job
+    case = getter()
+    # site-list semantics for both (fresh deletion queue per region) so the raw dumps are comparable
+    _, odump, owarn = cases.run_oracle(case, flags, site_list=True)
+    _, edump, ewarn, _ = cases.run_engine(case, flags, site_list=True, want_dump=True)
+    assert edump == odump, _first_diff(edump, odump)
+    assert (ewarn[0], ewarn[1], ewarn[3]) == owarn
