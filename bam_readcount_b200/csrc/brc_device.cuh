@@ -14,7 +14,7 @@
 
 namespace brc {
 
-constexpr int TILE = 128;            // sites per CTA of the pileup kernel (threads = sites)
+constexpr int TILE = 256;            // sites per CTA of the pileup kernel (threads = sites)
 constexpr int N_STATS = 13;
 constexpr uint32_t LIB_NONE = 0xFFFFu;
 constexpr int KIND_INS = 6, KIND_DEL = 7;
@@ -27,33 +27,41 @@ constexpr uint32_t FLAG_FILTER = 4u | 256u | 512u | 1024u;
 constexpr uint32_t FM_SIMPLE = 1u << 24;     // CIGAR has exactly one ref-consuming op, of match type, and no I/D/N/P
 constexpr uint32_t FM_NM_ABSENT = 1u << 25;  // NM tag missing -> NM_TAG_MISSING warning per process_read
 constexpr uint32_t FM_SM_MISSING = 1u << 26; // proper pair without SM tag -> SM_TAG_MISSING warning per process_read
+constexpr uint32_t FM_FASTDIV = 1u << 27;    // 1 <= l_qseq, clipped_length <= FASTDIV_MAX: reciprocal division is exact (tests)
+constexpr int FASTDIV_MAX = 2048;
 
 struct __align__(16) ReadDesc {
     // q0
     int32_t pos;        // leftmost reference position
     int32_t end;        // bam_endpos (== pos for reads the pileup buffer never admits)
-    int32_t l_qseq;
     uint32_t fm;        // flag | mapq<<16 | FM_* bits
-    // q1 : the five values of fetch_func (R:bamreadcount.cpp:248-253)
+    uint32_t lib_nc;    // lib[0:16) | min(n_cigar,0xFFFF)<<16
+    // q1 : four of the five values of fetch_func (R:bamreadcount.cpp:248-253)
     int32_t mmq;        // sum_of_mismatch_qualities
     int32_t clen;       // clipped_length
     int32_t lclip;      // left_clip
     int32_t tpi;        // three_prime_index
     // q2
     int32_t q2;         // q2_pos
-    float nmfrac;       // (float)NM / (float)clipped_length   (R:BasicStat.cpp:97), 0 if NM absent
+    float nmfrac;       // (float)NM / (float)clipped_length   (R:BasicStat.cpp:97), +0 if NM absent
     int32_t se;         // contribution to sum_single_ended_map_qualities (R:BasicStat.cpp:78-91)
-    uint32_t lib_nc;    // lib[0:16) | min(n_cigar,0xFFFF)<<16
+    int32_t l_qseq;
     // q3
-    uint64_t seq_off;   // byte offset of this read's packed bases
-    uint64_t qual_off;  // byte offset of this read's qualities
-    // q4
-    int32_t qoff;       // SIMPLE reads: qpos = site - pos + qoff
-    uint32_t cigar_off; // index of first CIGAR op
+    uint32_t qual32;    // low 32 bits of the read's byte offset in the qual pool
+    uint32_t seq32;     // low 32 bits of the read's byte offset in the seq pool
+    uint32_t cig;       // SIMPLE: qoff (qpos = site - pos + qoff); else index of the first CIGAR op
     uint32_t n_cigar;
-    uint32_t pad;
+    // q4
+    float rcp_l;        // RN(1 / (float)l_qseq)         (FM_FASTDIV only)
+    float rcp_clen;     // RN(1 / (float)clipped_length) (FM_FASTDIV only)
+    uint32_t pad0, pad1;
 };
 static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
+
+// K1 shared-memory staging: capacity of ONE slot of the 2-stage TMA ring
+constexpr int STAGE_READS = 96;                 // descriptors per chunk
+constexpr int STAGE_QUAL = 12288 + 32;          // staged quality bytes per chunk (incl. 16-B alignment slack both ends)
+constexpr int STAGE_SEQ = 6144 + 32;            // staged packed-base bytes per chunk
 
 struct TileInfo {
     int32_t pos0;       // absolute position of the tile's first site
@@ -119,8 +127,10 @@ struct PileupParams {
     int32_t min_mapq, min_bq, per_lib, insertion_centric;
     const ReadDesc *desc;
     const uint32_t *cigar;
-    const uint8_t *seq;
-    const uint8_t *qual;
+    const uint8_t *seq;       // 16-byte aligned, >= 16 readable bytes past the last read
+    const uint8_t *qual;      // 16-byte aligned, >= 16 readable bytes past the last read
+    const uint64_t *seq_off;  // [n_reads+1]
+    const uint64_t *qual_off; // [n_reads+1]
     const TileInfo *tiles;
     const int32_t *tile_lo;
     const int32_t *tile_hi;
@@ -144,5 +154,6 @@ cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tile
                               unsigned long long *warn, cudaStream_t s);
 cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s);
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s);
+cudaError_t launch_fastmath_selftest(int max_b, unsigned long long *d_bad, cudaStream_t s);
 
 }  // namespace brc

@@ -286,6 +286,7 @@ static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStrea
     PileupParams P1{};
     P1.min_mapq = e->cfg.min_mapq; P1.min_bq = e->cfg.min_bq; P1.per_lib = e->cfg.per_lib; P1.insertion_centric = e->cfg.insertion_centric;
     P1.desc = e->d_desc.as<ReadDesc>(); P1.cigar = e->dev_reads.cigar; P1.seq = e->dev_reads.seq; P1.qual = e->dev_reads.qual;
+    P1.seq_off = e->dev_reads.seq_off; P1.qual_off = e->dev_reads.qual_off;
     P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size();
     P1.res = results_dev(e);
 
@@ -478,6 +479,20 @@ int brc_fetch_device_results(brc_engine *e, void *stream) {
 }
 
 int brc_last_launch_count(const brc_engine *e) { return e ? e->launch_count : 0; }
+
+int64_t brc_selftest_fastmath(brc_engine *e, int32_t max_b) {
+    if (!e || max_b < 1) return BRC_E_INVALID;
+    cudaSetDevice(e->cfg.device);
+    unsigned long long *d_bad = nullptr, h_bad = 0;
+    CU(cudaMalloc(&d_bad, 8), "cudaMalloc");
+    cudaMemsetAsync(d_bad, 0, 8, e->stream);
+    cudaError_t ce = launch_fastmath_selftest(max_b, d_bad, e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d_bad);
+    if (ce != cudaSuccess) return set_cuda_error(e, ce, "fastmath selftest");
+    return (int64_t)h_bad;
+}
 float brc_last_stage_ms(const brc_engine *e, int stage) {
     if (!e || stage < 0 || stage > 2) return 0.0f;
     // events were recorded on the launching stream around K0 and K1; wait for the last one

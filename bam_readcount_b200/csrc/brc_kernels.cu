@@ -18,6 +18,8 @@
 //
 // All float arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction, no
 // fast-math): the results must match the reference's x86-64 SSE arithmetic bit for bit.
+#include <algorithm>
+
 #include "brc_device.cuh"
 
 namespace brc {
@@ -170,6 +172,8 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
     int32_t se;
     if (flag & 2u) { if (sm != INT32_MIN) se = sm; else { se = 0; fm |= FM_SM_MISSING; } }
     else se = (int32_t)mapq;
+    const bool fast = l_qseq >= 1 && l_qseq <= FASTDIV_MAX && clipped_length >= 1 && clipped_length <= FASTDIV_MAX;
+    if (fast) fm |= FM_FASTDIV;
     d.fm = fm;
     d.mmq = (int32_t)sum_mmq; d.clen = clipped_length; d.lclip = left_clip; d.tpi = tpi;
     d.q2 = q2_pos;
@@ -177,8 +181,11 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
     d.se = se;
     const uint32_t lib = R.lib ? (uint32_t)R.lib[i] : 0u;
     d.lib_nc = lib | ((n_cigar > 0xFFFFu ? 0xFFFFu : n_cigar) << 16);
-    d.seq_off = soff; d.qual_off = qoffb;
-    d.qoff = qoff; d.cigar_off = (uint32_t)coff; d.n_cigar = n_cigar; d.pad = 0;
+    d.qual32 = (uint32_t)qoffb; d.seq32 = (uint32_t)soff;
+    d.cig = simple ? (uint32_t)qoff : (uint32_t)coff; d.n_cigar = n_cigar;
+    d.rcp_l = fast ? __frcp_rn((float)l_qseq) : 0.0f;
+    d.rcp_clen = fast ? __frcp_rn((float)clipped_length) : 0.0f;
+    d.pad0 = 0; d.pad1 = 0;
     // 5 x 16-byte stores
     int4 *dst = reinterpret_cast<int4 *>(P.desc + i);
     const int4 *src = reinterpret_cast<const int4 *>(&d);
@@ -212,53 +219,116 @@ cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: site-centric pileup + ordered accumulation
+// K1: site-centric pileup + ordered accumulation.
+//
+// Persistent, warp-specialised CTAs: warp 8 is the PRODUCER — it walks this CTA's
+// tiles, cuts each tile's position-sorted read range into chunks and streams every chunk
+// (descriptors + quality bytes + packed bases) into a 2-stage shared-memory ring with bulk-TMA copies
+// that complete on an mbarrier; warps 0-7 are CONSUMERS — thread = site, each warp walks the staged
+// reads in file order and accumulates in registers.  full/empty mbarriers are the only
+// synchronisation, so chunk i+1 is in flight while chunk i is being consumed.
 // ---------------------------------------------------------------------------------------------
-struct Acc {  // the 13 accumulators, print order (BRC_S_*)
-    uint32_t count, mapq, baseq, se, plus, minus;
-    float posf, nmf;
+constexpr int N_CONSUMER_WARPS = TILE / 32;
+constexpr int K1_THREADS = TILE + 32;
+constexpr int NSTAGE = 2;
+
+struct Acc {  // 13 accumulators in registers (print order BRC_S_*); minus strand = count - plus
+    uint32_t count, mapq, baseq, se, plus;
+    float nmf;
     uint32_t mmqs, nq2;
     float q2d;
     uint32_t clip;
     float d3p;
-};
-struct Event {  // one (site, read) event's contributions (computed once, used for base and indel keys)
-    uint32_t mapq, baseq, mmq, clen;
-    int32_t se;
-    bool minus, has_q2;
-    float q2term, d3pterm, nmterm;
-    double posterm;   // 1.0 - |(qpos-left_clip) - rc| / rc   evaluated in double (R:BasicStat.cpp:70)
+    double posd;  // sum_event_location, always holding a float32-representable value
 };
 
-__device__ __forceinline__ void acc_zero(Acc &a) {
-    a.count = a.mapq = a.baseq = a.se = a.plus = a.minus = a.mmqs = a.nq2 = a.clip = 0;
-    a.posf = a.nmf = a.q2d = a.d3p = 0.0f;
+// RN_f32(x) as a double, for finite |x| in the float32 normal range, without F2F conversions:
+// adding and subtracting C = 2^(e+29) (e = exponent of x) rounds x to 24 significant bits, ties to even.
+__device__ __forceinline__ double round_to_f32_precision(double x) {
+    const int hi = __double2hiint(x);
+    const double c = __hiloint2double((hi & 0x7ff00000) + (29 << 20), 0);   // sign dropped: |C| = 2^(e+29)
+    const double cs = hi < 0 ? -c : c;
+    return __dsub_rn(__dadd_rn(x, cs), cs);
 }
-__device__ __forceinline__ void acc_add(Acc &a, const Event &e, bool is_indel) {
-    a.count++;
-    a.mapq += e.mapq;
-    if (e.minus) a.minus++; else a.plus++;
-    a.mmqs += e.mmq;
-    if (e.has_q2) { a.q2d = __fadd_rn(a.q2d, e.q2term); a.nq2++; }
-    a.d3p = __fadd_rn(a.d3p, e.d3pterm);
-    a.clip += e.clen;
-    a.posf = __double2float_rn(__dadd_rn((double)a.posf, e.posterm));
-    a.se += (uint32_t)e.se;
-    a.nmf = __fadd_rn(a.nmf, e.nmterm);
-    if (!is_indel) a.baseq += e.baseq;
+// exact float32 -> float64 for finite, non-denormal f >= 0 (and +0) by bit manipulation
+__device__ __forceinline__ double f32_to_f64_nonneg(float f) {
+    const uint32_t b = __float_as_uint(f);
+    const uint32_t hi = b == 0u ? 0u : (b >> 3) + (896u << 20);
+    return __hiloint2double((int)hi, (int)(b << 29));
+}
+// RN(a / b) for small non-negative integer-valued a and positive integer-valued b <= FASTDIV_MAX with rcp = RN(1/b):
+// one Newton step on the product (Markstein); verified exhaustively against __fdiv_rn by the GPU tests.
+__device__ __forceinline__ float div_small(float a, float b, float rcp) {
+    const float q0 = __fmul_rn(a, rcp);
+    const float r = __fmaf_rn(-b, q0, a);
+    return __fmaf_rn(r, rcp, q0);
 }
 
-// secondary key record: find-or-append in the thread's private chain, then accumulate in place
-__device__ __noinline__ void sec_accumulate(const PileupParams &P, int32_t &head, int kind, int len, int64_t read,
-                                            int qpos, const Event &e, bool is_indel) {
+// One (site, read) event's contributions — the body of BasicStat::process_read (R:BasicStat.cpp:28-107).
+struct Terms { float q2term, d3pterm; double posterm; };
+__device__ __forceinline__ Terms event_terms(bool fast, int qpos, int q2pos, int tpi, int lclip, int clen, int l_qseq,
+                                             float rcp_l, float rcp_c) {
+    Terms t;
+    const float fl = (float)l_qseq;
+    const float a_q2 = (float)abs(qpos - q2pos), a_3p = (float)abs(qpos - tpi);
+    if (fast) {
+        t.q2term = div_small(a_q2, fl, rcp_l);
+        t.d3pterm = div_small(a_3p, fl, rcp_l);
+        // |(qpos-lclip) - clen/2| / (clen/2)  ==  |2(qpos-lclip) - clen| / clen   (numerator and denominator exact)
+        const float f = div_small((float)abs(2 * (qpos - lclip) - clen), (float)clen, rcp_c);
+        t.posterm = __dsub_rn(1.0, f32_to_f64_nonneg(f));
+    } else {
+        t.q2term = __fdiv_rn(a_q2, fl);
+        t.d3pterm = __fdiv_rn(a_3p, fl);
+        const float rc = __fmul_rn((float)clen, 0.5f);
+        const float f = __fdiv_rn(fabsf(__fsub_rn((float)(qpos - lclip), rc)), rc);
+        t.posterm = __dsub_rn(1.0, (double)f);
+    }
+    return t;
+}
+
+// stateless resolve_cigar2.  Returns {qpos, indel, is_del}.
+__device__ __noinline__ int3 resolve_general(const uint32_t *cig, uint32_t n_cigar, int32_t pos, int32_t site) {
+    int64_t x = pos; int y = 0; uint32_t k = 0; uint32_t op = 0; int len = 0;
+    for (; k < n_cigar; ++k) {
+        const uint32_t c = cig[k]; op = c & 0xFu; len = (int)(c >> 4);
+        if (is_refop(op)) {
+            if ((int64_t)site < x + len) break;
+            x += len; if (is_matchop(op)) y += len;
+        } else if (op == 1 || op == 4) y += len;
+    }
+    int3 out = make_int3(0, 0, 0);
+    if (k >= n_cigar) { out.z = 1; return out; }  // cannot happen for pos <= site < end
+    if (is_matchop(op)) out.x = y + (int)(site - x); else { out.z = 1; out.x = y; }
+    if (x + len - 1 == site && k + 1 < n_cigar) {
+        const uint32_t c2 = cig[k + 1]; const uint32_t op2 = c2 & 0xFu; const int l2 = (int)(c2 >> 4);
+        if (op2 == 2) out.y = -l2;
+        else if (op2 == 1) out.y = l2;
+        else if (op2 == 6 && k + 2 < n_cigar) {
+            int l3 = 0;
+            for (uint32_t m = k + 2; m < n_cigar; ++m) {
+                const uint32_t c3 = cig[m]; const uint32_t op3 = c3 & 0xFu;
+                if (op3 == 1) l3 += (int)(c3 >> 4);
+                else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
+            }
+            if (l3 > 0) out.y = l3;
+        }
+    }
+    return out;
+}
+
+// Rare keys (indel alleles, a third base class at a site): find-or-append a record in the thread's private
+// chain in the L2-resident pool and accumulate there.  Recomputes the event from the global descriptor so
+// the hot loop carries no state for it.  Returns the new chain head.
+__device__ __noinline__ int32_t rare_event(const PileupParams &P, int32_t head, int kind, int len, int32_t read, int qpos,
+                                           uint32_t bq, bool is_indel) {
     const ResultsDev &S = P.res;
     int32_t j = head;
     while (j >= 0) {
         if (S.sec_kind[j] == (uint8_t)kind && S.sec_len[j] == len) {
             if (kind != KIND_INS) break;
             // same inserted bases?  compare canonicalised read bases (R:bamreadcount.cpp:324-330)
-            const ReadDesc *da = P.desc + read, *db = P.desc + S.sec_read[j];
-            const uint64_t oa = da->seq_off, ob = db->seq_off;
+            const uint64_t oa = P.seq_off[read], ob = P.seq_off[S.sec_read[j]];
             const int qb = S.sec_qpos[j];
             bool same = true;
             for (int k = 1; k <= len && same; ++k)
@@ -269,164 +339,342 @@ __device__ __noinline__ void sec_accumulate(const PileupParams &P, int32_t &head
     }
     if (j < 0) {
         j = atomicAdd(S.sec_count, 1);
-        if ((int64_t)j >= S.sec_cap) return;   // overflow: host sees sec_count > cap and retries with a larger pool
+        if ((int64_t)j >= S.sec_cap) return head;   // overflow: host sees sec_count > cap and retries with a larger pool
         S.sec_next[j] = head; S.sec_kind[j] = (uint8_t)kind; S.sec_len[j] = len; S.sec_read[j] = read; S.sec_qpos[j] = qpos;
 #pragma unroll
         for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = 0u;
         head = j;
     }
+    const ReadDesc d = P.desc[read];
+    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.l_qseq, 0.f, 0.f);
     uint32_t *st = S.sec_stats + j;
     const int64_t c = S.sec_cap;
     st[0 * c] += 1u;
-    st[1 * c] += e.mapq;
-    if (!is_indel) st[2 * c] += e.baseq;
-    st[3 * c] += (uint32_t)e.se;
-    if (e.minus) st[5 * c] += 1u; else st[4 * c] += 1u;
-    st[6 * c] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(st[6 * c]), e.posterm)));
-    st[7 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[7 * c]), e.nmterm));
-    st[8 * c] += e.mmq;
-    if (e.has_q2) { st[9 * c] += 1u; st[10 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[10 * c]), e.q2term)); }
-    st[11 * c] += e.clen;
-    st[12 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[12 * c]), e.d3pterm));
+    st[1 * c] += (d.fm >> 16) & 0xFFu;
+    if (!is_indel) st[2 * c] += bq;
+    st[3 * c] += (uint32_t)d.se;
+    if (d.fm & 16u) st[5 * c] += 1u; else st[4 * c] += 1u;
+    st[6 * c] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(st[6 * c]), t.posterm)));
+    st[7 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[7 * c]), d.nmfrac));
+    st[8 * c] += (uint32_t)d.mmq;
+    if (d.q2 > -1) { st[9 * c] += 1u; st[10 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[10 * c]), t.q2term)); }
+    st[11 * c] += (uint32_t)d.clen;
+    st[12 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[12 * c]), t.d3pterm));
+    return head;
 }
 
-// stateless resolve_cigar2: which op holds `site`, qpos, is_del, indel
-__device__ __noinline__ void resolve_general(const uint32_t *cig, uint32_t n_cigar, int32_t pos, int32_t site, int &qpos,
-                                             int &indel, bool &is_del) {
-    int64_t x = pos; int y = 0; uint32_t k = 0; uint32_t op = 0; int len = 0;
-    for (; k < n_cigar; ++k) {
-        const uint32_t c = cig[k]; op = c & 0xFu; len = (int)(c >> 4);
-        if (is_refop(op)) {
-            if ((int64_t)site < x + len) break;
-            x += len; if (is_matchop(op)) y += len;
-        } else if (op == 1 || op == 4) y += len;
-    }
-    indel = 0; is_del = false; qpos = 0;
-    if (k >= n_cigar) { is_del = true; return; }  // cannot happen for pos <= site < end
-    if (is_matchop(op)) qpos = y + (int)(site - x); else { is_del = true; qpos = y; }
-    if (x + len - 1 == site && k + 1 < n_cigar) {
-        const uint32_t c2 = cig[k + 1]; const uint32_t op2 = c2 & 0xFu; const int l2 = (int)(c2 >> 4);
-        if (op2 == 2) indel = -l2;
-        else if (op2 == 1) indel = l2;
-        else if (op2 == 6 && k + 2 < n_cigar) {
-            int l3 = 0;
-            for (uint32_t m = k + 2; m < n_cigar; ++m) {
-                const uint32_t c3 = cig[m]; const uint32_t op3 = c3 & 0xFu;
-                if (op3 == 1) l3 += (int)(c3 >> 4);
-                else if (op3 == 2 || op3 == 0 || op3 == 3 || op3 == 7 || op3 == 8) break;
-            }
-            if (l3 > 0) indel = l3;
-        }
-    }
+// --- mbarrier / bulk-TMA primitives (PTX; SASS: SYNCS.*, UBLKCP) ---
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// global -> shared bulk copy through the TMA unit; completes on `bar` with `bytes` transaction bytes.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct __align__(16) ChunkInfo {
+    int32_t work;        // work item (row * n_tiles + tile), -1 = no more work
+    int32_t r0, r1;      // reads [r0, r1) staged in this slot
+    uint32_t qbase32, sbase32;
+    uint32_t flags;      // bit0 staged (qual/seq in smem), bit1 first chunk of the tile, bit2 last chunk of the tile
+    int32_t pos0, n;     // TileInfo
+    int64_t slot0;
+    uint32_t row, pad;
+};
+struct __align__(128) StageBuf {
+    int4 desc[STAGE_READS * 5];
+    uint8_t qual[STAGE_QUAL];
+    uint8_t seq[STAGE_SEQ];
+};
+struct __align__(128) PileupSmem {
+    StageBuf st[NSTAGE];
+    uint32_t sacc[N_STATS][TILE];   // second base class of each site (stat-major: conflict-free)
+    ChunkInfo info[NSTAGE];
+    uint64_t full[NSTAGE], empty[NSTAGE];
+};
 
 template <bool PER_LIB>
-__global__ void __launch_bounds__(TILE) pileup_kernel(PileupParams P) {
-    const int64_t tile = blockIdx.x;
-    const uint32_t row = blockIdx.y;
-    const TileInfo ti = P.tiles[tile];
-    const int sl = threadIdx.x;
-    const bool active = sl < ti.n;
-    const int32_t site = ti.pos0 + sl;
-    const int32_t lo = P.tile_lo[tile], hi = P.tile_hi[tile];
-    const int warp0 = sl & ~31;
-    const int32_t wfirst = ti.pos0 + warp0;
-    const int32_t wlast = ti.pos0 + min(warp0 + 31, ti.n - 1);
-    if (warp0 >= ti.n) return;   // whole warp beyond the tile
+__global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    PileupSmem &sm = *reinterpret_cast<PileupSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int64_t n_work = P.n_tiles * (int64_t)P.res.n_rows;
 
-    Acc acc; acc_zero(acc);
-    uint32_t ncover = 0, npass = 0, flags = 0, pbase = NO_BASE;
-    int32_t sec_head = -1;
-    uint32_t warn_sm = 0, warn_nm = 0;
-    const int4 *desc4 = reinterpret_cast<const int4 *>(P.desc);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], N_CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    for (int32_t r = lo; r < hi; ++r) {
-        const int4 q0 = __ldg(desc4 + (int64_t)r * 5 + 0);       // pos,end,l_qseq,fm
-        if (q0.x > wlast) break;                                 // reads are position-sorted within a region
-        if (q0.y <= wfirst) continue;
-        const int4 q2 = __ldg(desc4 + (int64_t)r * 5 + 2);       // q2,nmfrac,se,lib_nc
-        const bool cover = active && site >= q0.x && site < q0.y;
-        if (PER_LIB) {
-            const uint32_t lib = (uint32_t)q2.w & 0xFFFFu;
-            if (lib == LIB_NONE) { if (cover) flags |= 1u; continue; }
-            if (lib != row) continue;
-            // -p: pileup_func returns at the first read without a library (R:...:281-284); nothing after
-            // it in pileup (= file) order is processed or warned about at this site
-            if (flags & 1u) continue;
+    if (warp == N_CONSUMER_WARPS) {
+        // =========================== PRODUCER ===========================
+        if (lane != 0) return;
+        uint32_t item = 0;
+        for (int64_t w = blockIdx.x;; w += gridDim.x) {
+            const bool done = w >= n_work;
+            int32_t lo = 0, hi = 0; TileInfo ti{0, 0, 0}; uint32_t row = 0;
+            if (!done) {
+                const int64_t tile = w % P.n_tiles; row = (uint32_t)(w / P.n_tiles);
+                ti = P.tiles[tile]; lo = P.tile_lo[tile]; hi = P.tile_hi[tile];
+                if (lo >= hi) { lo = 0; hi = 0; }
+            }
+            int32_t r0 = lo;
+            bool first = true;
+            do {
+                const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
+                mbar_wait(&sm.empty[s], ph ^ 1u);          // consumers released this slot
+                ChunkInfo ci{};
+                ci.work = done ? -1 : (int32_t)w;
+                ci.pos0 = ti.pos0; ci.n = ti.n; ci.slot0 = ti.slot0; ci.row = row;
+                uint32_t bytes = 0;
+                int32_t r1 = r0;
+                if (r0 < hi) {
+                    r1 = min(r0 + STAGE_READS, hi);
+                    uint64_t qa, qb, sa, sb; bool staged;
+                    for (;;) {   // as many reads as fit the stage
+                        qa = P.qual_off[r0] & ~15ull; qb = (P.qual_off[r1] + 15ull) & ~15ull;
+                        sa = P.seq_off[r0] & ~15ull;  sb = (P.seq_off[r1] + 15ull) & ~15ull;
+                        staged = (qb - qa) <= (uint64_t)STAGE_QUAL && (sb - sa) <= (uint64_t)STAGE_SEQ;
+                        if (staged || r1 - r0 == 1) break;
+                        r1 = r0 + (r1 - r0) / 2;
+                    }
+                    const uint32_t db = (uint32_t)(r1 - r0) * (uint32_t)sizeof(ReadDesc);
+                    const uint32_t qbytes = staged ? (uint32_t)(qb - qa) : 0u, sbytes = staged ? (uint32_t)(sb - sa) : 0u;
+                    bytes = db + qbytes + sbytes;
+                    ci.qbase32 = (uint32_t)qa; ci.sbase32 = (uint32_t)sa;
+                    ci.flags = staged ? 1u : 0u;
+                    ci.r0 = r0; ci.r1 = r1;
+                    ci.flags |= (first ? 2u : 0u) | (r1 >= hi ? 4u : 0u);
+                    sm.info[s] = ci;
+                    mbar_expect_tx(&sm.full[s], bytes);
+                    tma_bulk_g2s(sm.st[s].desc, P.desc + r0, db, &sm.full[s]);
+                    if (qbytes) tma_bulk_g2s(sm.st[s].qual, P.qual + qa, qbytes, &sm.full[s]);
+                    if (sbytes) tma_bulk_g2s(sm.st[s].seq, P.seq + sa, sbytes, &sm.full[s]);
+                } else {   // tile without reads, or the terminator
+                    ci.r0 = ci.r1 = 0; ci.flags = 2u | 4u;
+                    sm.info[s] = ci;
+                    mbar_arrive(&sm.full[s]);
+                }
+                item++; first = false; r0 = r1;
+            } while (r0 < hi);
+            if (done) break;
         }
-        if (!cover) continue;
-        ncover++;
-        const uint32_t fm = (uint32_t)q0.w;
-        const int4 q3 = __ldg(desc4 + (int64_t)r * 5 + 3);       // seq_off, qual_off
-        const int4 q4 = __ldg(desc4 + (int64_t)r * 5 + 4);       // qoff,cigar_off,n_cigar
-        const uint64_t seq_off = ((uint64_t)(uint32_t)q3.y << 32) | (uint32_t)q3.x;
-        const uint64_t qual_off = ((uint64_t)(uint32_t)q3.w << 32) | (uint32_t)q3.z;
-        int qpos, indel = 0; bool is_del = false;
-        if (fm & FM_SIMPLE) qpos = site - q0.x + q4.x;
-        else resolve_general(P.cigar + (uint32_t)q4.y, (uint32_t)q4.z, q0.x, site, qpos, indel, is_del);
-        if (is_del) continue;
-        const uint32_t mapq = (fm >> 16) & 0xFFu;
-        if ((int)mapq < P.min_mapq) continue;
-        const uint32_t bq = P.qual[qual_off + (uint32_t)qpos];
-        if ((int)bq < P.min_bq) continue;
-        if (fm & FLAG_FILTER) continue;
-        npass++;
-
-        const int4 q1 = __ldg(desc4 + (int64_t)r * 5 + 1);       // mmq,clen,lclip,tpi
-        Event e;
-        e.mapq = mapq; e.baseq = bq; e.mmq = (uint32_t)q1.x; e.clen = (uint32_t)q1.y; e.se = q2.z;
-        e.minus = (fm & 16u) != 0;
-        const float fl = (float)q0.z;
-        e.has_q2 = q2.x > -1;
-        e.q2term = e.has_q2 ? __fdiv_rn((float)abs(qpos - q2.x), fl) : 0.0f;
-        e.d3pterm = __fdiv_rn((float)abs(qpos - q1.w), fl);
-        e.nmterm = __int_as_float(q2.y);
-        const float rc = __fmul_rn((float)q1.y, 0.5f);
-        const float f = __fdiv_rn(fabsf(__fsub_rn((float)(qpos - q1.z), rc)), rc);
-        e.posterm = __dsub_rn(1.0, (double)f);
-        const bool nm_absent = (fm & FM_NM_ABSENT) != 0, sm_missing = (fm & FM_SM_MISSING) != 0;
-        if (nm_absent) e.nmterm = 0.0f;
-
-        if (indel != 0) {
-            sec_accumulate(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, (int64_t)r, qpos, e, true);
-            warn_nm += nm_absent; warn_sm += sm_missing;
-        }
-        if (indel < 1 || !P.insertion_centric) {
-            const uint32_t base = canonical16(seq_nib(P.seq, seq_off, qpos));
-            if (pbase == NO_BASE) pbase = base;
-            if (base == pbase) {
-                acc_add(acc, e, false);   // NM missing: nmterm is +0.0f, which leaves the float sum unchanged
-            } else sec_accumulate(P, sec_head, (int)base, 0, (int64_t)r, qpos, e, false);
-            warn_nm += nm_absent; warn_sm += sm_missing;
-        }
+        return;
     }
 
-    if (active) {
-        const ResultsDev &S = P.res;
-        const int64_t idx = (int64_t)row * S.n_slots + ti.slot0 + sl;
-        const int64_t stride = (int64_t)S.n_rows * S.n_slots;
-        S.ncover[idx] = ncover; S.npass[idx] = npass; S.flags[idx] = (uint8_t)flags; S.pbase[idx] = (uint8_t)pbase;
-        S.sec_head[idx] = sec_head;
-        uint32_t *ps = S.pstats + idx;
-        ps[0 * stride] = acc.count; ps[1 * stride] = acc.mapq; ps[2 * stride] = acc.baseq; ps[3 * stride] = acc.se;
-        ps[4 * stride] = acc.plus; ps[5 * stride] = acc.minus; ps[6 * stride] = __float_as_uint(acc.posf);
-        ps[7 * stride] = __float_as_uint(acc.nmf); ps[8 * stride] = acc.mmqs; ps[9 * stride] = acc.nq2;
-        ps[10 * stride] = __float_as_uint(acc.q2d); ps[11 * stride] = acc.clip; ps[12 * stride] = __float_as_uint(acc.d3p);
+    // =========================== CONSUMERS ===========================
+    Acc acc;
+    uint32_t ncover = 0, npass = 0, flags = 0, pbase = NO_BASE, sbase = NO_BASE;
+    int32_t sec_head = -1;
+    uint32_t warn_sm = 0, warn_nm = 0;
+    bool active = false, warp_done = false;
+    int32_t site = 0, wfirst = 0, wlast = 0;
+    const int warp0 = tid & ~31;
+
+    for (uint32_t item = 0;; ++item) {
+        const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
+        mbar_wait(&sm.full[s], ph);
+        const ChunkInfo ci = sm.info[s];
+        if (ci.work < 0) break;
+        const StageBuf &sb = sm.st[s];
+        if (ci.flags & 2u) {   // first chunk of a tile: reset the per-site state
+            acc.count = acc.mapq = acc.baseq = acc.se = acc.plus = acc.mmqs = acc.nq2 = acc.clip = 0;
+            acc.nmf = acc.q2d = acc.d3p = 0.0f; acc.posd = 0.0;
+            ncover = npass = flags = 0; pbase = sbase = NO_BASE; sec_head = -1;
+            active = tid < ci.n; site = ci.pos0 + tid;
+            wfirst = ci.pos0 + warp0; wlast = ci.pos0 + min(warp0 + 31, ci.n - 1);
+            warp_done = warp0 >= ci.n;
+        }
+        const bool staged = (ci.flags & 1u) != 0;
+        if (!warp_done) {
+            const int n_in = ci.r1 - ci.r0;
+            for (int i = 0; i < n_in; ++i) {
+                const int4 *ds = sb.desc + i * 5;
+                const int4 q0 = ds[0];                                   // pos,end,fm,lib_nc
+                if (q0.x > wlast) { warp_done = true; break; }           // reads are position-sorted within a region
+                if (q0.y <= wfirst) continue;
+                const bool cover = active && site >= q0.x && site < q0.y;
+                if (PER_LIB) {
+                    const uint32_t lib = (uint32_t)q0.w & 0xFFFFu;
+                    if (lib == LIB_NONE) { if (cover) flags |= 1u; continue; }
+                    if (lib != ci.row) continue;
+                    // -p: pileup_func returns at the first read without a library (R:...:281-284); nothing after
+                    // it in pileup (= file) order is processed or warned about at this site
+                    if (flags & 1u) continue;
+                }
+                if (!cover) continue;
+                ncover++;
+                const uint32_t fm = (uint32_t)q0.z;
+                const int4 q3 = ds[3];                                   // qual32,seq32,cig,n_cigar
+                int qpos, indel = 0;
+                if (fm & FM_SIMPLE) qpos = site - q0.x + q3.z;
+                else {
+                    const int3 rr = resolve_general(P.cigar + (uint32_t)q3.z, (uint32_t)q3.w, q0.x, site);
+                    if (rr.z) continue;                                  // is_del
+                    qpos = rr.x; indel = rr.y;
+                }
+                const uint32_t mapq = (fm >> 16) & 0xFFu;
+                if ((int)mapq < P.min_mapq) continue;
+                const int32_t r = ci.r0 + i;
+                uint32_t bq;
+                if (staged) bq = sb.qual[((uint32_t)q3.x - ci.qbase32) + (uint32_t)qpos];
+                else bq = P.qual[P.qual_off[r] + (uint32_t)qpos];
+                if ((int)bq < P.min_bq) continue;
+                if (fm & FLAG_FILTER) continue;
+                npass++;
+                const uint32_t nm_absent = (fm & FM_NM_ABSENT) ? 1u : 0u, sm_missing = (fm & FM_SM_MISSING) ? 1u : 0u;
+                if (indel != 0) {
+                    sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
+                    warn_nm += nm_absent; warn_sm += sm_missing;
+                    if (indel > 0 && P.insertion_centric) continue;
+                }
+                warn_nm += nm_absent; warn_sm += sm_missing;
+                uint32_t nib;
+                if (staged) { const uint32_t b = sb.seq[((uint32_t)q3.y - ci.sbase32) + ((uint32_t)qpos >> 1)]; nib = (qpos & 1) ? (b & 0xFu) : (b >> 4); }
+                else nib = seq_nib(P.seq, P.seq_off[r], qpos);
+                const uint32_t base = canonical16(nib);
+                if (pbase == NO_BASE) pbase = base;
+                if (base != pbase && sbase != NO_BASE && base != sbase) {   // third base class at this site: rare
+                    sec_head = rare_event(P, sec_head, (int)base, 0, r, qpos, bq, false);
+                    continue;
+                }
+                const int4 q1 = ds[1];                                   // mmq,clen,lclip,tpi
+                const int4 q2 = ds[2];                                   // q2,nmfrac,se,l_qseq
+                const int4 q4 = ds[4];                                   // rcp_l, rcp_clen
+                const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, q2.x, q1.w, q1.z, q1.y, q2.w, __int_as_float(q4.x), __int_as_float(q4.y));
+                const bool has_q2 = q2.x > -1;
+                const uint32_t plus = (fm & 16u) ? 0u : 1u;
+                const float nmterm = __int_as_float(q2.y);
+                if (base == pbase) {
+                    acc.count++; acc.mapq += mapq; acc.plus += plus; acc.mmqs += (uint32_t)q1.x;
+                    if (has_q2) { acc.q2d = __fadd_rn(acc.q2d, t.q2term); acc.nq2++; }
+                    acc.d3p = __fadd_rn(acc.d3p, t.d3pterm);
+                    acc.clip += (uint32_t)q1.y;
+                    acc.posd = round_to_f32_precision(__dadd_rn(acc.posd, t.posterm));
+                    acc.se += (uint32_t)q2.z;
+                    acc.nmf = __fadd_rn(acc.nmf, nmterm);
+                    acc.baseq += bq;
+                } else {   // second base class of the site: accumulators live in shared memory
+                    uint32_t (*A)[TILE] = sm.sacc;
+                    if (sbase == NO_BASE) {
+                        sbase = base;
+#pragma unroll
+                        for (int k = 0; k < N_STATS; ++k) A[k][tid] = 0u;
+                    }
+                    A[0][tid] += 1u; A[1][tid] += mapq; A[2][tid] += bq; A[3][tid] += (uint32_t)q2.z;
+                    A[4][tid] += plus; A[5][tid] += 1u - plus;
+                    A[6][tid] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(A[6][tid]), t.posterm)));
+                    A[7][tid] = __float_as_uint(__fadd_rn(__uint_as_float(A[7][tid]), nmterm));
+                    A[8][tid] += (uint32_t)q1.x;
+                    if (has_q2) { A[9][tid] += 1u; A[10][tid] = __float_as_uint(__fadd_rn(__uint_as_float(A[10][tid]), t.q2term)); }
+                    A[11][tid] += (uint32_t)q1.y;
+                    A[12][tid] = __float_as_uint(__fadd_rn(__uint_as_float(A[12][tid]), t.d3pterm));
+                }
+            }
+        }
+        if (ci.flags & 4u) {   // last chunk of the tile: emit the sites
+            const ResultsDev &S = P.res;
+            if (active) {
+                if (sbase != NO_BASE) {   // move the second base class into the record pool
+                    const int32_t j = atomicAdd(S.sec_count, 1);
+                    if ((int64_t)j < S.sec_cap) {
+                        S.sec_next[j] = sec_head; S.sec_kind[j] = (uint8_t)sbase; S.sec_len[j] = 0; S.sec_read[j] = 0; S.sec_qpos[j] = 0;
+#pragma unroll
+                        for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = sm.sacc[k][tid];
+                        sec_head = j;
+                    }
+                }
+                const int64_t idx = (int64_t)ci.row * S.n_slots + ci.slot0 + tid;
+                const int64_t stride = (int64_t)S.n_rows * S.n_slots;
+                S.ncover[idx] = ncover; S.npass[idx] = npass; S.flags[idx] = (uint8_t)flags; S.pbase[idx] = (uint8_t)pbase;
+                S.sec_head[idx] = sec_head;
+                uint32_t *ps = S.pstats + idx;
+                ps[0 * stride] = acc.count; ps[1 * stride] = acc.mapq; ps[2 * stride] = acc.baseq; ps[3 * stride] = acc.se;
+                ps[4 * stride] = acc.plus; ps[5 * stride] = acc.count - acc.plus; ps[6 * stride] = __float_as_uint(__double2float_rn(acc.posd));
+                ps[7 * stride] = __float_as_uint(acc.nmf); ps[8 * stride] = acc.mmqs; ps[9 * stride] = acc.nq2;
+                ps[10 * stride] = __float_as_uint(acc.q2d); ps[11 * stride] = acc.clip; ps[12 * stride] = __float_as_uint(acc.d3p);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);   // this warp is done with the slot
     }
     // warning counters: warp-reduce then one atomic per warp
     for (int o = 16; o; o >>= 1) { warn_sm += __shfl_xor_sync(0xffffffffu, warn_sm, o); warn_nm += __shfl_xor_sync(0xffffffffu, warn_nm, o); }
-    if ((sl & 31) == 0) {
+    if (lane == 0) {
         if (warn_sm) atomicAdd(P.res.warn + 0, (unsigned long long)warn_sm);
         if (warn_nm) atomicAdd(P.res.warn + 1, (unsigned long long)warn_nm);
     }
 }
 
+static int g_sm_count[64] = {0};
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
     if (p.n_tiles == 0) return cudaSuccess;
-    // grid.x is limited to 2^31-1 tiles; grid.y = library rows
-    dim3 grid((unsigned)p.n_tiles, (unsigned)p.res.n_rows, 1);
-    if (p.per_lib) pileup_kernel<true><<<grid, TILE, 0, s>>>(p);
-    else pileup_kernel<false><<<grid, TILE, 0, s>>>(p);
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 64 && g_sm_count[dev] == 0) {
+        cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e1 = cudaFuncSetAttribute(pileup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PileupSmem));
+        cudaError_t e2 = cudaFuncSetAttribute(pileup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PileupSmem));
+        if (e1 != cudaSuccess) return e1;
+        if (e2 != cudaSuccess) return e2;
+    }
+    const int sms = dev < 64 && g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
+    const int64_t n_work = p.n_tiles * (int64_t)p.res.n_rows;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_work, (int64_t)sms * 3);   // persistent: 3 CTAs per SM
+    const size_t smem = sizeof(PileupSmem);
+    if (p.per_lib) pileup_kernel<true><<<grid, K1_THREADS, smem, s>>>(p);
+    else pileup_kernel<false><<<grid, K1_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-test: div_small / round_to_f32_precision / f32_to_f64_nonneg against the IEEE intrinsics
+// ---------------------------------------------------------------------------------------------
+__global__ void fastmath_selftest_kernel(int max_b, unsigned long long *bad) {
+    const int b = blockIdx.x + 1;
+    if (b > max_b) return;
+    const float fb = (float)b, rcp = __frcp_rn(fb);
+    unsigned long long nbad = 0;
+    for (int a = threadIdx.x; a <= 2 * b + 2; a += blockDim.x) {
+        const float fa = (float)a;
+        const float want = __fdiv_rn(fa, fb), got = div_small(fa, fb, rcp);
+        if (__float_as_uint(want) != __float_as_uint(got)) nbad++;
+        // 1 - f in double, added to a float-valued running sum, rounded back to float
+        const double t_want = __dsub_rn(1.0, (double)want), t_got = __dsub_rn(1.0, f32_to_f64_nonneg(want));
+        if (__double_as_longlong(t_want) != __double_as_longlong(t_got)) nbad++;
+        for (int k = 0; k < 4; ++k) {
+            const float s = __fmul_rn((float)(a * 7 + k * 131 + b), k == 3 ? -0.37f : 0.618034f);
+            const double x = __dadd_rn((double)s, t_want);
+            const float r_want = __double2float_rn(x);
+            const double r_got = round_to_f32_precision(x);
+            if ((double)r_want != r_got) nbad++;
+        }
+    }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
+cudaError_t launch_fastmath_selftest(int max_b, unsigned long long *d_bad, cudaStream_t s) {
+    fastmath_selftest_kernel<<<max_b, 128, 0, s>>>(max_b, d_bad);
     return cudaGetLastError();
 }
 

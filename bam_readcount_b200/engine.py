@@ -61,7 +61,7 @@ EXPORTS = [
     "brc_abi_version", "brc_create", "brc_destroy", "brc_last_error", "brc_strerror", "brc_set_reference", "brc_reset",
     "brc_begin_region", "brc_push_read", "brc_push_reads", "brc_end_region", "brc_compute", "brc_get_results",
     "brc_get_warning_counts", "brc_format_text", "brc_plan_device", "brc_run_device", "brc_device_results",
-    "brc_fetch_device_results", "brc_last_launch_count", "brc_last_stage_ms",
+    "brc_fetch_device_results", "brc_last_launch_count", "brc_last_stage_ms", "brc_selftest_fastmath",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.brc_run_device.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p]
     lib.brc_device_results.argtypes = [C.c_void_p, C.POINTER(CResults)]
     lib.brc_fetch_device_results.argtypes = [C.c_void_p, C.c_void_p]
+    lib.brc_selftest_fastmath.argtypes = [C.c_void_p, C.c_int32]
+    lib.brc_selftest_fastmath.restype = C.c_int64
     lib.brc_last_launch_count.argtypes = [C.c_void_p]
     lib.brc_last_stage_ms.argtypes = [C.c_void_p, C.c_int]
     lib.brc_last_stage_ms.restype = C.c_float

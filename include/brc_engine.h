@@ -117,9 +117,10 @@ typedef struct {
     const uint64_t *cigar_off;  /* [n_reads+1] offsets into cigar */
     const uint32_t *cigar;      /* bam1_cigar(b): len<<4|op */
     const uint64_t *seq_off;    /* [n_reads+1] byte offsets into seq */
-    const uint8_t *seq;         /* bam1_seq(b): 4-bit packed, (l_qseq+1)/2 bytes per read */
+    const uint8_t *seq;         /* bam1_seq(b): 4-bit packed, (l_qseq+1)/2 bytes per read.  Device batches: pool base
+                                 * 16-byte aligned with >= 16 readable bytes after the last read (bulk-TMA staging) */
     const uint64_t *qual_off;   /* [n_reads+1] byte offsets into qual */
-    const uint8_t *qual;        /* bam1_qual(b) */
+    const uint8_t *qual;        /* bam1_qual(b); device batches: same alignment/padding rule as seq */
 } brc_read_batch;
 
 /* One region of the reference's loops: compute sites [beg-1, end), print [beg, end). */
@@ -208,6 +209,9 @@ BRC_API int brc_plan_device(brc_engine *e, const brc_region *regions, int64_t n_
 BRC_API int brc_run_device(brc_engine *e, const brc_read_batch *dev_batch, const int32_t *dev_region_of_read, void *stream);
 BRC_API int brc_device_results(brc_engine *e, brc_results *out);
 BRC_API int brc_fetch_device_results(brc_engine *e, void *stream);
+/* Self-test of the kernels' exact-arithmetic shortcuts (reciprocal division, float<->double bit casts)
+ * against the IEEE intrinsics for every divisor 1..max_b; returns the number of mismatches (0 = ok). */
+BRC_API int64_t brc_selftest_fastmath(brc_engine *e, int32_t max_b);
 /* kernels launched by the last brc_run_device/brc_compute (for bench.py's gpu_launches) */
 BRC_API int brc_last_launch_count(const brc_engine *e);
 /* elapsed GPU milliseconds of the named stage of the last run, measured with CUDA events on the

@@ -40,3 +40,14 @@ def test_engine_accumulators_match_oracle_bit_exact(job):
     _, edump, ewarn, _ = cases.run_engine(case, flags, site_list=True, want_dump=True)
     assert edump == odump, _first_diff(edump, odump)
     assert (ewarn[0], ewarn[1], ewarn[3]) == owarn
+
+
+def test_exact_arithmetic_shortcuts_match_ieee_intrinsics():
+    """K1 replaces __fdiv_rn by a reciprocal + one FMA correction and float<->double conversions by bit
+    casts for read lengths <= 2048; every (numerator, divisor) pair it can see must agree with IEEE."""
+    from bam_readcount_b200.engine import Engine
+    e = Engine()
+    try:
+        assert e.lib.brc_selftest_fastmath(e.h, 2048) == 0
+    finally:
+        e.close()
