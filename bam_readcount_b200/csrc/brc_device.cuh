@@ -45,7 +45,7 @@ struct __align__(16) ReadDesc {
     int32_t q2;         // q2_pos
     float nmfrac;       // (float)NM / (float)clipped_length   (R:BasicStat.cpp:97), +0 if NM absent
     int32_t se;         // contribution to sum_single_ended_map_qualities (R:BasicStat.cpp:78-91)
-    int32_t l_qseq;
+    float fl;           // (float)l_qseq
     // q3
     uint32_t qual32;    // low 32 bits of the read's byte offset in the qual pool
     uint32_t seq32;     // low 32 bits of the read's byte offset in the seq pool
@@ -54,7 +54,8 @@ struct __align__(16) ReadDesc {
     // q4
     float rcp_l;        // RN(1 / (float)l_qseq)         (FM_FASTDIV only)
     float rcp_clen;     // RN(1 / (float)clipped_length) (FM_FASTDIV only)
-    uint32_t pad0, pad1;
+    float fclen;        // (float)clipped_length
+    uint32_t pad1;
 };
 static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
 
@@ -79,7 +80,7 @@ struct RegionDev {
 };
 
 struct RefWin {
-    const char *seq;    // device pointer, seq[0] = position win_beg
+    const char *seq;    // device pointer to 4-bit reference CODES (seq_nt16_table of the FASTA characters), [0] = position win_beg
     int64_t chrom_len;
     int64_t win_beg;
     int64_t win_len;
@@ -153,6 +154,7 @@ struct PrecomputeParams {
 cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tiles, int32_t *sec_count,
                               unsigned long long *warn, cudaStream_t s);
 cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s);
+cudaError_t launch_ref_encode(const char *d_ascii, uint8_t *d_code, int64_t n, cudaStream_t s);
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s);
 cudaError_t launch_fastmath_selftest(int max_b, unsigned long long *d_bad, cudaStream_t s);
 

@@ -93,8 +93,15 @@ int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64
     r->tid = tid; r->name = contig_name ? contig_name : ""; r->chrom_len = chrom_len; r->win_beg = win_beg; r->win_len = win_len;
     r->seq.assign(seq, (size_t)win_len);
     CU(r->dev.reserve((size_t)win_len + 16), "cudaMalloc(reference)");
-    CU(cudaMemcpyAsync(r->dev.p, r->seq.data(), (size_t)win_len, cudaMemcpyHostToDevice, e->stream), "H2D reference");
-    CU(cudaStreamSynchronize(e->stream), "sync reference");
+    {   // upload the FASTA characters, keep only their 4-bit codes on the device (K0 compares nibbles)
+        DevBuf ascii;
+        CU(ascii.reserve((size_t)win_len + 16), "cudaMalloc(reference ascii)");
+        cudaError_t ce = cudaMemcpyAsync(ascii.p, r->seq.data(), (size_t)win_len, cudaMemcpyHostToDevice, e->stream);
+        if (ce == cudaSuccess) ce = launch_ref_encode(ascii.as<char>(), r->dev.as<uint8_t>(), win_len, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        ascii.release();
+        if (ce != cudaSuccess) return set_cuda_error(e, ce, "reference upload/encode");
+    }
     // refresh the device RefWin table
     std::vector<RefWin> tab(e->refs.size());
     for (size_t i = 0; i < e->refs.size(); ++i)

@@ -70,31 +70,129 @@ cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tile
 }
 
 // ---------------------------------------------------------------------------------------------
-// K0: per-read precompute.  One thread per read (v0).
+// reference window: ASCII -> 4-bit codes, once per brc_set_reference (part of load_reference, not of a step)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ char ref_at(const RefWin &rw, int64_t p) {
-    if (p < 0 || p >= rw.chrom_len) return 0;          // the reference's string ends with NUL at chrom_len
-    if (p < rw.win_beg || p >= rw.win_beg + rw.win_len) return 'N';
-    return rw.seq[p - rw.win_beg];
+__global__ void ref_encode_kernel(const char *ascii, uint8_t *code, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) code[i] = c_nt16[(unsigned char)ascii[i]];
 }
 
-__global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= P.reads.n_reads) return;
-    const ReadsDev &R = P.reads;
-    int32_t g = P.region_of_read ? P.region_of_read[i] : 0;
-    const RegionDev rg = P.regions[g];
-    const RefWin rw = P.refs[rg.tid_slot];
+static cudaError_t ensure_tables() {
+    if (!h_nt16_ready) build_nt16();
+    static bool uploaded[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 64 && !uploaded[dev]) {
+        cudaError_t e = cudaMemcpyToSymbol(c_nt16, h_nt16, 256);
+        if (e != cudaSuccess) return e;
+        uploaded[dev] = true;
+    }
+    return cudaSuccess;
+}
 
-    const int32_t pos = R.pos[i];
-    const uint32_t flag = R.flag[i];
-    const uint32_t mapq = R.mapq[i];
-    const int32_t l_qseq = R.l_qseq[i];
-    const uint64_t coff = R.cigar_off[i];
-    const uint32_t n_cigar = (uint32_t)(R.cigar_off[i + 1] - coff);
+cudaError_t launch_ref_encode(const char *d_ascii, uint8_t *d_code, int64_t n, cudaStream_t s) {
+    cudaError_t e = ensure_tables();
+    if (e != cudaSuccess || n == 0) return e;
+    ref_encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_ascii, d_code, n);
+    return cudaGetLastError();
+}
+
+// --- mbarrier / bulk-TMA primitives (PTX; SASS: SYNCS.*, UBLKCP) ---
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// producer-side wait: long suspend-time hint so the idle producer lane does not burn issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITR_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONER_%=;\n"
+        "bra WAITR_%=;\n"
+        "DONER_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(20000u) : "memory");
+}
+// global -> shared bulk copy through the TMA unit; completes on `bar` with `bytes` transaction bytes.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: per-read precompute.  One CTA = K0_READS consecutive reads; their packed bases and
+// qualities (two contiguous byte ranges of the pools) are staged in shared memory by bulk TMA,
+// then one thread walks one read.  Reference codes come straight from global memory: reads are
+// position-sorted, so a warp's 32 walks touch one or two 128-byte lines per step.
+// ---------------------------------------------------------------------------------------------
+constexpr int K0_READS = 128;
+constexpr int K0_SEQ_CAP = K0_READS * 80 + 32;
+constexpr int K0_QUAL_CAP = K0_READS * 160 + 32;
+struct __align__(128) K0Smem {
+    uint8_t seq[K0_SEQ_CAP];
+    uint8_t qual[K0_QUAL_CAP];
+    uint64_t bar;
+};
+
+__global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputeParams P) {
+    __shared__ K0Smem ks;
+    const ReadsDev &R = P.reads;
+    const int64_t r0 = blockIdx.x * (int64_t)K0_READS;
+    const int64_t r1 = min(r0 + (int64_t)K0_READS, R.n_reads);
+    const int64_t i = r0 + threadIdx.x;
+
+    // stage the block's byte ranges (uniform decision)
+    const uint64_t qa = R.qual_off[r0] & ~15ull, qb = (R.qual_off[r1] + 15ull) & ~15ull;
+    const uint64_t sa = R.seq_off[r0] & ~15ull, sb = (R.seq_off[r1] + 15ull) & ~15ull;
+    const bool staged = (qb - qa) <= (uint64_t)K0_QUAL_CAP && (sb - sa) <= (uint64_t)K0_SEQ_CAP;
+    if (staged) {
+        if (threadIdx.x == 0) {
+            mbar_init(&ks.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&ks.bar, (uint32_t)(qb - qa) + (uint32_t)(sb - sa));
+            tma_bulk_g2s(ks.qual, R.qual + qa, (uint32_t)(qb - qa), &ks.bar);
+            tma_bulk_g2s(ks.seq, R.seq + sa, (uint32_t)(sb - sa), &ks.bar);
+        }
+        __syncthreads();   // barrier initialised before anyone waits on it
+    }
+    const bool live = i < r1;
+    // per-read scalars: coalesced global loads, overlapped with the bulk copies
+    int32_t pos = 0, l_qseq = 0, nm = 0, smtag = 0; uint32_t flag = 0, mapq = 0, lib = 0, n_cigar = 0;
+    uint64_t coff = 0, soff = 0, qoffb = 0;
+    RegionDev rg{}; RefWin rw{};
+    if (live) {
+        const int32_t g = P.region_of_read ? P.region_of_read[i] : 0;
+        rg = P.regions[g]; rw = P.refs[rg.tid_slot];
+        pos = R.pos[i]; flag = R.flag[i]; mapq = R.mapq[i]; l_qseq = R.l_qseq[i]; nm = R.nm[i]; smtag = R.sm[i];
+        lib = R.lib ? (uint32_t)R.lib[i] : 0u;
+        coff = R.cigar_off[i]; n_cigar = (uint32_t)(R.cigar_off[i + 1] - coff);
+        soff = R.seq_off[i]; qoffb = R.qual_off[i];
+    }
+    if (staged) mbar_wait(&ks.bar, 0);
+    if (!live) return;
     const uint32_t *cig = R.cigar + coff;
-    const uint64_t soff = R.seq_off[i], qoffb = R.qual_off[i];
-    const uint8_t *qual = R.qual + qoffb;
+    // generic pointers: shared memory when staged, the global pools otherwise (reads too long for the stage)
+    const uint8_t *seq = staged ? (ks.seq + (soff - sa)) : (R.seq + soff);
+    const uint8_t *qual = staged ? (ks.qual + (qoffb - qa)) : (R.qual + qoffb);
+    const uint8_t *refc = reinterpret_cast<const uint8_t *>(rw.seq);   // 4-bit codes (launch_ref_encode)
 
     // --- fetch_func CIGAR/reference walk (R:...:133-199) + bam_cigar2rlen + SIMPLE detection ---
     uint32_t sum_mmq = 0;
@@ -115,16 +213,21 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
         else if (op == 4 && !seen_ref) qoff += op_length;
         if (!walking) continue;
         if (op == 0) {
-            int j;
-            for (j = 0; j < op_length; ++j) {
+            // positions whose reference base exists: [0, jn); at refpos == chrom_len the reference string's NUL stops the walk
+            int jn = op_length;
+            bool hit_nul = false;
+            if (reference_position + op_length > rw.chrom_len) {
+                if (rg.ref_len_check && reference_position > rw.chrom_len) jn = 0;   // -l mode: every position is skipped (R:...:144-148)
+                else { const int64_t room = rw.chrom_len - reference_position; jn = room > 0 ? (int)room : 0; hit_nul = true; }
+            }
+            const int64_t wrel = reference_position - rw.win_beg;
+            for (int j = 0; j < jn; ++j) {
                 const int cur = read_position + j;
-                const int64_t refpos = reference_position + j;
-                if (rg.ref_len_check && refpos > rw.chrom_len) continue;
-                const char rc = ref_at(rw, refpos);
-                if (rc == 0) break;
-                const uint32_t ref_base = c_nt16[(unsigned char)rc];
-                const uint32_t read_base = seq_nib(R.seq, soff, cur);
-                if (read_base != ref_base && ref_base != 15 && read_base != 0) {
+                const int64_t w = wrel + j;
+                const uint32_t ref_base = (w >= 0 && w < rw.win_len) ? refc[w] : 15u;   // outside the supplied window: 'N'
+                const uint32_t b = seq[cur >> 1];
+                const uint32_t read_base = (cur & 1) ? (b & 0xFu) : (b >> 4);
+                if (read_base != ref_base && ref_base != 15u && read_base != 0u) {
                     const int q = qual[cur];
                     if (last_mm_pos != -1) {
                         if (last_mm_pos + 1 != cur) { sum_mmq += (uint32_t)last_mm_qual; last_mm_qual = q; }
@@ -133,7 +236,8 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
                     } else { last_mm_pos = cur; last_mm_qual = q; }
                 }
             }
-            if (j < op_length) { walking = false; continue; }
+            // site-list mode skips positions beyond chrom_len (R:...:144-148) but position == chrom_len still reads the NUL
+            if (hit_nul) { walking = false; continue; }
             reference_position += op_length; read_position += op_length;
         } else if (op == 2 || op == 3) reference_position += op_length;
         else if (op == 1) read_position += op_length;
@@ -158,16 +262,15 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
     else { if (tpi > q2_pos && q2_pos != -1) tpi = q2_pos; }
 
     // --- admission (bam_plp_push) and span (bam_endpos) ---
-    const int32_t tid_ok = 1;  // tid<0 reads are dropped by the host batcher / caller contract
     const bool unmapped = (flag & 4u) != 0;
     int64_t end = (!unmapped && n_cigar > 0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
-    if (unmapped || !tid_ok) end = pos;      // never admitted to the pileup: covers nothing
+    if (unmapped) end = pos;      // never admitted to the pileup: covers nothing
 
     ReadDesc d;
-    d.pos = pos; d.end = (int32_t)end; d.l_qseq = l_qseq;
+    d.pos = pos; d.end = (int32_t)end; d.fl = (float)l_qseq;
     uint32_t fm = (flag & 0xFFFFu) | (mapq << 16);
     if (simple) fm |= FM_SIMPLE;
-    const int32_t nm = R.nm[i], sm = R.sm[i];
+    const int32_t sm = smtag;
     if (nm == INT32_MIN) fm |= FM_NM_ABSENT;
     int32_t se;
     if (flag & 2u) { if (sm != INT32_MIN) se = sm; else { se = 0; fm |= FM_SM_MISSING; } }
@@ -179,13 +282,12 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
     d.q2 = q2_pos;
     d.nmfrac = (nm == INT32_MIN) ? 0.0f : __fdiv_rn((float)nm, (float)clipped_length);
     d.se = se;
-    const uint32_t lib = R.lib ? (uint32_t)R.lib[i] : 0u;
     d.lib_nc = lib | ((n_cigar > 0xFFFFu ? 0xFFFFu : n_cigar) << 16);
     d.qual32 = (uint32_t)qoffb; d.seq32 = (uint32_t)soff;
     d.cig = simple ? (uint32_t)qoff : (uint32_t)coff; d.n_cigar = n_cigar;
     d.rcp_l = fast ? __frcp_rn((float)l_qseq) : 0.0f;
     d.rcp_clen = fast ? __frcp_rn((float)clipped_length) : 0.0f;
-    d.pad0 = 0; d.pad1 = 0;
+    d.fclen = (float)clipped_length; d.pad1 = 0;
     // 5 x 16-byte stores
     int4 *dst = reinterpret_cast<int4 *>(P.desc + i);
     const int4 *src = reinterpret_cast<const int4 *>(&d);
@@ -204,17 +306,10 @@ __global__ void __launch_bounds__(128) read_precompute_kernel(PrecomputeParams P
 }
 
 cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s) {
-    if (!h_nt16_ready) build_nt16();
-    static bool uploaded[64] = {false};
-    int dev = 0; cudaGetDevice(&dev);
-    if (dev < 64 && !uploaded[dev]) {
-        cudaError_t e = cudaMemcpyToSymbol(c_nt16, h_nt16, 256);
-        if (e != cudaSuccess) return e;
-        uploaded[dev] = true;
-    }
+    cudaError_t e = ensure_tables();
+    if (e != cudaSuccess) return e;
     if (p.reads.n_reads == 0) return cudaSuccess;
-    const int bs = 128;
-    read_precompute_kernel<<<(unsigned)((p.reads.n_reads + bs - 1) / bs), bs, 0, s>>>(p);
+    read_precompute_kernel<<<(unsigned)((p.reads.n_reads + K0_READS - 1) / K0_READS), K0_READS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -246,9 +341,8 @@ struct Acc {  // 13 accumulators in registers (print order BRC_S_*); minus stran
 // adding and subtracting C = 2^(e+29) (e = exponent of x) rounds x to 24 significant bits, ties to even.
 __device__ __forceinline__ double round_to_f32_precision(double x) {
     const int hi = __double2hiint(x);
-    const double c = __hiloint2double((hi & 0x7ff00000) + (29 << 20), 0);   // sign dropped: |C| = 2^(e+29)
-    const double cs = hi < 0 ? -c : c;
-    return __dsub_rn(__dadd_rn(x, cs), cs);
+    const double c = __hiloint2double((hi & (int)0xfff00000) + (29 << 20), 0);   // copysign(2^(e+29), x)
+    return __dsub_rn(__dadd_rn(x, c), c);
 }
 // exact float32 -> float64 for finite, non-denormal f >= 0 (and +0) by bit manipulation
 __device__ __forceinline__ double f32_to_f64_nonneg(float f) {
@@ -266,21 +360,20 @@ __device__ __forceinline__ float div_small(float a, float b, float rcp) {
 
 // One (site, read) event's contributions — the body of BasicStat::process_read (R:BasicStat.cpp:28-107).
 struct Terms { float q2term, d3pterm; double posterm; };
-__device__ __forceinline__ Terms event_terms(bool fast, int qpos, int q2pos, int tpi, int lclip, int clen, int l_qseq,
+__device__ __forceinline__ Terms event_terms(bool fast, int qpos, int q2pos, int tpi, int lclip, int clen, float fl, float fclen,
                                              float rcp_l, float rcp_c) {
     Terms t;
-    const float fl = (float)l_qseq;
     const float a_q2 = (float)abs(qpos - q2pos), a_3p = (float)abs(qpos - tpi);
     if (fast) {
         t.q2term = div_small(a_q2, fl, rcp_l);
         t.d3pterm = div_small(a_3p, fl, rcp_l);
         // |(qpos-lclip) - clen/2| / (clen/2)  ==  |2(qpos-lclip) - clen| / clen   (numerator and denominator exact)
-        const float f = div_small((float)abs(2 * (qpos - lclip) - clen), (float)clen, rcp_c);
+        const float f = div_small((float)abs(2 * (qpos - lclip) - clen), fclen, rcp_c);
         t.posterm = __dsub_rn(1.0, f32_to_f64_nonneg(f));
     } else {
         t.q2term = __fdiv_rn(a_q2, fl);
         t.d3pterm = __fdiv_rn(a_3p, fl);
-        const float rc = __fmul_rn((float)clen, 0.5f);
+        const float rc = __fmul_rn(fclen, 0.5f);
         const float f = __fdiv_rn(fabsf(__fsub_rn((float)(qpos - lclip), rc)), rc);
         t.posterm = __dsub_rn(1.0, (double)f);
     }
@@ -346,7 +439,7 @@ __device__ __noinline__ int32_t rare_event(const PileupParams &P, int32_t head, 
         head = j;
     }
     const ReadDesc d = P.desc[read];
-    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.l_qseq, 0.f, 0.f);
+    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, 0.f, 0.f);
     uint32_t *st = S.sec_stats + j;
     const int64_t c = S.sec_cap;
     st[0 * c] += 1u;
@@ -361,35 +454,6 @@ __device__ __noinline__ int32_t rare_event(const PileupParams &P, int32_t head, 
     st[11 * c] += (uint32_t)d.clen;
     st[12 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[12 * c]), t.d3pterm));
     return head;
-}
-
-// --- mbarrier / bulk-TMA primitives (PTX; SASS: SYNCS.*, UBLKCP) ---
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-// global -> shared bulk copy through the TMA unit; completes on `bar` with `bytes` transaction bytes.
-// dst/src 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 struct __align__(16) ChunkInfo {
@@ -412,6 +476,147 @@ struct __align__(128) PileupSmem {
     ChunkInfo info[NSTAGE];
     uint64_t full[NSTAGE], empty[NSTAGE];
 };
+
+// per-thread (= per-site) state of a consumer, all in registers
+struct SiteState {
+    Acc acc;
+    uint32_t ncover, npass, flags, pbase, sbase;
+    int32_t sec_head;
+    uint32_t warn_sm = 0, warn_nm = 0;
+    bool active, warp_done;
+    int32_t site, wfirst, wlast;
+    int tid, warp0;
+};
+__device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci) {
+    Acc &a = S.acc;
+    a.count = a.mapq = a.baseq = a.se = a.plus = a.mmqs = a.nq2 = a.clip = 0;
+    a.nmf = a.q2d = a.d3p = 0.0f; a.posd = 0.0;
+    S.ncover = S.npass = S.flags = 0; S.pbase = S.sbase = NO_BASE; S.sec_head = -1;
+    S.active = S.tid < ci.n; S.site = ci.pos0 + S.tid;
+    S.wfirst = ci.pos0 + S.warp0; S.wlast = ci.pos0 + min(S.warp0 + 31, ci.n - 1);
+    S.warp_done = S.warp0 >= ci.n;
+}
+
+// The hot loop: one warp walks the chunk's reads in file order; lane = site.
+template <bool PER_LIB, bool STAGED>
+__device__ __forceinline__ void process_chunk(const PileupParams &P, const StageBuf &sb, uint32_t (*sacc)[TILE], const ChunkInfo &ci,
+                                              SiteState &S) {
+    const int n_in = ci.r1 - ci.r0;
+    const int4 *ds = sb.desc;
+    const uint8_t *qual_s = sb.qual - ci.qbase32;   // staged bytes are addressed with the reads' low-32 pool offsets
+    const uint8_t *seq_s = sb.seq - ci.sbase32;
+    const int tid = S.tid;
+    for (int i = 0; i < n_in; ++i, ds += 5) {
+        const int4 q0 = ds[0];                                   // pos,end,fm,lib_nc
+        if (q0.x > S.wlast) { S.warp_done = true; break; }       // reads are position-sorted within a region
+        if (q0.y <= S.wfirst) continue;
+        const bool cover = S.active && S.site >= q0.x && S.site < q0.y;
+        if (PER_LIB) {
+            const uint32_t lib = (uint32_t)q0.w & 0xFFFFu;
+            if (lib == LIB_NONE) { if (cover) S.flags |= 1u; continue; }
+            if (lib != ci.row) continue;
+            // -p: pileup_func returns at the first read without a library (R:...:281-284); nothing after
+            // it in pileup (= file) order is processed or warned about at this site
+            if (S.flags & 1u) continue;
+        }
+        if (!cover) continue;
+        S.ncover++;
+        const uint32_t fm = (uint32_t)q0.z;
+        const int4 q3 = ds[3];                                   // qual32,seq32,cig,n_cigar
+        int qpos, indel = 0;
+        if (fm & FM_SIMPLE) qpos = S.site - q0.x + q3.z;
+        else {
+            const int3 rr = resolve_general(P.cigar + (uint32_t)q3.z, (uint32_t)q3.w, q0.x, S.site);
+            if (rr.z) continue;                                  // is_del
+            qpos = rr.x; indel = rr.y;
+        }
+        const uint32_t mapq = (fm >> 16) & 0xFFu;
+        if ((int)mapq < P.min_mapq) continue;
+        const int32_t r = ci.r0 + i;
+        uint32_t bq;
+        if (STAGED) bq = qual_s[(uint32_t)q3.x + (uint32_t)qpos];
+        else bq = P.qual[P.qual_off[r] + (uint32_t)qpos];
+        if ((int)bq < P.min_bq) continue;
+        if (fm & FLAG_FILTER) continue;
+        S.npass++;
+        const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // rare: a tag the reference warns about is missing
+        if (indel != 0) {
+            S.sec_head = rare_event(P, S.sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
+            if (warns) { S.warn_nm += (fm & FM_NM_ABSENT) ? 1u : 0u; S.warn_sm += (fm & FM_SM_MISSING) ? 1u : 0u; }
+            if (indel > 0 && P.insertion_centric) continue;
+        }
+        if (warns) { S.warn_nm += (fm & FM_NM_ABSENT) ? 1u : 0u; S.warn_sm += (fm & FM_SM_MISSING) ? 1u : 0u; }
+        uint32_t byte;
+        if (STAGED) byte = seq_s[(uint32_t)q3.y + ((uint32_t)qpos >> 1)];
+        else byte = P.seq[P.seq_off[r] + ((uint32_t)qpos >> 1)];
+        const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
+        if (S.pbase == NO_BASE) S.pbase = base;
+        if (base != S.pbase && S.sbase != NO_BASE && base != S.sbase) {   // third base class at this site: rare
+            S.sec_head = rare_event(P, S.sec_head, (int)base, 0, r, qpos, bq, false);
+            continue;
+        }
+        const int4 q1 = ds[1];                                   // mmq,clen,lclip,tpi
+        const int4 q2 = ds[2];                                   // q2,nmfrac,se,fl
+        const int4 q4 = ds[4];                                   // rcp_l, rcp_clen, fclen
+        const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, q2.x, q1.w, q1.z, q1.y, __int_as_float(q2.w), __int_as_float(q4.z),
+                                    __int_as_float(q4.x), __int_as_float(q4.y));
+        const bool has_q2 = q2.x > -1;
+        const uint32_t plus = (fm & 16u) ? 0u : 1u;
+        const float nmterm = __int_as_float(q2.y);
+        if (base == S.pbase) {
+            Acc &a = S.acc;
+            a.count++; a.mapq += mapq; a.plus += plus; a.mmqs += (uint32_t)q1.x;
+            if (has_q2) { a.q2d = __fadd_rn(a.q2d, t.q2term); a.nq2++; }
+            a.d3p = __fadd_rn(a.d3p, t.d3pterm);
+            a.clip += (uint32_t)q1.y;
+            a.posd = round_to_f32_precision(__dadd_rn(a.posd, t.posterm));
+            a.se += (uint32_t)q2.z;
+            a.nmf = __fadd_rn(a.nmf, nmterm);
+            a.baseq += bq;
+        } else {   // second base class of the site: accumulators live in shared memory
+            if (S.sbase == NO_BASE) {
+                S.sbase = base;
+#pragma unroll
+                for (int k = 0; k < N_STATS; ++k) sacc[k][tid] = 0u;
+            }
+            sacc[0][tid] += 1u; sacc[1][tid] += mapq; sacc[2][tid] += bq; sacc[3][tid] += (uint32_t)q2.z;
+            sacc[4][tid] += plus; sacc[5][tid] += 1u - plus;
+            sacc[6][tid] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(sacc[6][tid]), t.posterm)));
+            sacc[7][tid] = __float_as_uint(__fadd_rn(__uint_as_float(sacc[7][tid]), nmterm));
+            sacc[8][tid] += (uint32_t)q1.x;
+            if (has_q2) { sacc[9][tid] += 1u; sacc[10][tid] = __float_as_uint(__fadd_rn(__uint_as_float(sacc[10][tid]), t.q2term)); }
+            sacc[11][tid] += (uint32_t)q1.y;
+            sacc[12][tid] = __float_as_uint(__fadd_rn(__uint_as_float(sacc[12][tid]), t.d3pterm));
+        }
+    }
+}
+
+// last chunk of a tile: write the site's header + primary accumulators (coalesced SoA stores)
+__device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc)[TILE], const ChunkInfo &ci, SiteState &S) {
+    if (!S.active) return;
+    const ResultsDev &R = P.res;
+    const int tid = S.tid;
+    int32_t sec_head = S.sec_head;
+    if (S.sbase != NO_BASE) {   // move the second base class into the record pool
+        const int32_t j = atomicAdd(R.sec_count, 1);
+        if ((int64_t)j < R.sec_cap) {
+            R.sec_next[j] = sec_head; R.sec_kind[j] = (uint8_t)S.sbase; R.sec_len[j] = 0; R.sec_read[j] = 0; R.sec_qpos[j] = 0;
+#pragma unroll
+            for (int k = 0; k < N_STATS; ++k) R.sec_stats[(int64_t)k * R.sec_cap + j] = sacc[k][tid];
+            sec_head = j;
+        }
+    }
+    const int64_t idx = (int64_t)ci.row * R.n_slots + ci.slot0 + tid;
+    const int64_t stride = (int64_t)R.n_rows * R.n_slots;
+    const Acc &a = S.acc;
+    R.ncover[idx] = S.ncover; R.npass[idx] = S.npass; R.flags[idx] = (uint8_t)S.flags; R.pbase[idx] = (uint8_t)S.pbase;
+    R.sec_head[idx] = sec_head;
+    uint32_t *ps = R.pstats + idx;
+    ps[0 * stride] = a.count; ps[1 * stride] = a.mapq; ps[2 * stride] = a.baseq; ps[3 * stride] = a.se;
+    ps[4 * stride] = a.plus; ps[5 * stride] = a.count - a.plus; ps[6 * stride] = __float_as_uint(__double2float_rn(a.posd));
+    ps[7 * stride] = __float_as_uint(a.nmf); ps[8 * stride] = a.mmqs; ps[9 * stride] = a.nq2;
+    ps[10 * stride] = __float_as_uint(a.q2d); ps[11 * stride] = a.clip; ps[12 * stride] = __float_as_uint(a.d3p);
+}
 
 template <bool PER_LIB>
 __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
@@ -443,7 +648,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
             bool first = true;
             do {
                 const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
-                mbar_wait(&sm.empty[s], ph ^ 1u);          // consumers released this slot
+                mbar_wait_relaxed(&sm.empty[s], ph ^ 1u);  // consumers released this slot
                 ChunkInfo ci{};
                 ci.work = done ? -1 : (int32_t)w;
                 ci.pos0 = ti.pos0; ci.n = ti.n; ci.slot0 = ti.slot0; ci.row = row;
@@ -484,142 +689,24 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
     }
 
     // =========================== CONSUMERS ===========================
-    Acc acc;
-    uint32_t ncover = 0, npass = 0, flags = 0, pbase = NO_BASE, sbase = NO_BASE;
-    int32_t sec_head = -1;
-    uint32_t warn_sm = 0, warn_nm = 0;
-    bool active = false, warp_done = false;
-    int32_t site = 0, wfirst = 0, wlast = 0;
-    const int warp0 = tid & ~31;
-
+    SiteState S0;
+    S0.tid = tid; S0.warp0 = tid & ~31;
     for (uint32_t item = 0;; ++item) {
         const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
         mbar_wait(&sm.full[s], ph);
         const ChunkInfo ci = sm.info[s];
         if (ci.work < 0) break;
-        const StageBuf &sb = sm.st[s];
-        if (ci.flags & 2u) {   // first chunk of a tile: reset the per-site state
-            acc.count = acc.mapq = acc.baseq = acc.se = acc.plus = acc.mmqs = acc.nq2 = acc.clip = 0;
-            acc.nmf = acc.q2d = acc.d3p = 0.0f; acc.posd = 0.0;
-            ncover = npass = flags = 0; pbase = sbase = NO_BASE; sec_head = -1;
-            active = tid < ci.n; site = ci.pos0 + tid;
-            wfirst = ci.pos0 + warp0; wlast = ci.pos0 + min(warp0 + 31, ci.n - 1);
-            warp_done = warp0 >= ci.n;
+        if (ci.flags & 2u) site_reset(S0, ci);   // first chunk of a tile
+        if (!S0.warp_done) {
+            if (ci.flags & 1u) process_chunk<PER_LIB, true>(P, sm.st[s], sm.sacc, ci, S0);
+            else process_chunk<PER_LIB, false>(P, sm.st[s], sm.sacc, ci, S0);
         }
-        const bool staged = (ci.flags & 1u) != 0;
-        if (!warp_done) {
-            const int n_in = ci.r1 - ci.r0;
-            for (int i = 0; i < n_in; ++i) {
-                const int4 *ds = sb.desc + i * 5;
-                const int4 q0 = ds[0];                                   // pos,end,fm,lib_nc
-                if (q0.x > wlast) { warp_done = true; break; }           // reads are position-sorted within a region
-                if (q0.y <= wfirst) continue;
-                const bool cover = active && site >= q0.x && site < q0.y;
-                if (PER_LIB) {
-                    const uint32_t lib = (uint32_t)q0.w & 0xFFFFu;
-                    if (lib == LIB_NONE) { if (cover) flags |= 1u; continue; }
-                    if (lib != ci.row) continue;
-                    // -p: pileup_func returns at the first read without a library (R:...:281-284); nothing after
-                    // it in pileup (= file) order is processed or warned about at this site
-                    if (flags & 1u) continue;
-                }
-                if (!cover) continue;
-                ncover++;
-                const uint32_t fm = (uint32_t)q0.z;
-                const int4 q3 = ds[3];                                   // qual32,seq32,cig,n_cigar
-                int qpos, indel = 0;
-                if (fm & FM_SIMPLE) qpos = site - q0.x + q3.z;
-                else {
-                    const int3 rr = resolve_general(P.cigar + (uint32_t)q3.z, (uint32_t)q3.w, q0.x, site);
-                    if (rr.z) continue;                                  // is_del
-                    qpos = rr.x; indel = rr.y;
-                }
-                const uint32_t mapq = (fm >> 16) & 0xFFu;
-                if ((int)mapq < P.min_mapq) continue;
-                const int32_t r = ci.r0 + i;
-                uint32_t bq;
-                if (staged) bq = sb.qual[((uint32_t)q3.x - ci.qbase32) + (uint32_t)qpos];
-                else bq = P.qual[P.qual_off[r] + (uint32_t)qpos];
-                if ((int)bq < P.min_bq) continue;
-                if (fm & FLAG_FILTER) continue;
-                npass++;
-                const uint32_t nm_absent = (fm & FM_NM_ABSENT) ? 1u : 0u, sm_missing = (fm & FM_SM_MISSING) ? 1u : 0u;
-                if (indel != 0) {
-                    sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
-                    warn_nm += nm_absent; warn_sm += sm_missing;
-                    if (indel > 0 && P.insertion_centric) continue;
-                }
-                warn_nm += nm_absent; warn_sm += sm_missing;
-                uint32_t nib;
-                if (staged) { const uint32_t b = sb.seq[((uint32_t)q3.y - ci.sbase32) + ((uint32_t)qpos >> 1)]; nib = (qpos & 1) ? (b & 0xFu) : (b >> 4); }
-                else nib = seq_nib(P.seq, P.seq_off[r], qpos);
-                const uint32_t base = canonical16(nib);
-                if (pbase == NO_BASE) pbase = base;
-                if (base != pbase && sbase != NO_BASE && base != sbase) {   // third base class at this site: rare
-                    sec_head = rare_event(P, sec_head, (int)base, 0, r, qpos, bq, false);
-                    continue;
-                }
-                const int4 q1 = ds[1];                                   // mmq,clen,lclip,tpi
-                const int4 q2 = ds[2];                                   // q2,nmfrac,se,l_qseq
-                const int4 q4 = ds[4];                                   // rcp_l, rcp_clen
-                const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, q2.x, q1.w, q1.z, q1.y, q2.w, __int_as_float(q4.x), __int_as_float(q4.y));
-                const bool has_q2 = q2.x > -1;
-                const uint32_t plus = (fm & 16u) ? 0u : 1u;
-                const float nmterm = __int_as_float(q2.y);
-                if (base == pbase) {
-                    acc.count++; acc.mapq += mapq; acc.plus += plus; acc.mmqs += (uint32_t)q1.x;
-                    if (has_q2) { acc.q2d = __fadd_rn(acc.q2d, t.q2term); acc.nq2++; }
-                    acc.d3p = __fadd_rn(acc.d3p, t.d3pterm);
-                    acc.clip += (uint32_t)q1.y;
-                    acc.posd = round_to_f32_precision(__dadd_rn(acc.posd, t.posterm));
-                    acc.se += (uint32_t)q2.z;
-                    acc.nmf = __fadd_rn(acc.nmf, nmterm);
-                    acc.baseq += bq;
-                } else {   // second base class of the site: accumulators live in shared memory
-                    uint32_t (*A)[TILE] = sm.sacc;
-                    if (sbase == NO_BASE) {
-                        sbase = base;
-#pragma unroll
-                        for (int k = 0; k < N_STATS; ++k) A[k][tid] = 0u;
-                    }
-                    A[0][tid] += 1u; A[1][tid] += mapq; A[2][tid] += bq; A[3][tid] += (uint32_t)q2.z;
-                    A[4][tid] += plus; A[5][tid] += 1u - plus;
-                    A[6][tid] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(A[6][tid]), t.posterm)));
-                    A[7][tid] = __float_as_uint(__fadd_rn(__uint_as_float(A[7][tid]), nmterm));
-                    A[8][tid] += (uint32_t)q1.x;
-                    if (has_q2) { A[9][tid] += 1u; A[10][tid] = __float_as_uint(__fadd_rn(__uint_as_float(A[10][tid]), t.q2term)); }
-                    A[11][tid] += (uint32_t)q1.y;
-                    A[12][tid] = __float_as_uint(__fadd_rn(__uint_as_float(A[12][tid]), t.d3pterm));
-                }
-            }
-        }
-        if (ci.flags & 4u) {   // last chunk of the tile: emit the sites
-            const ResultsDev &S = P.res;
-            if (active) {
-                if (sbase != NO_BASE) {   // move the second base class into the record pool
-                    const int32_t j = atomicAdd(S.sec_count, 1);
-                    if ((int64_t)j < S.sec_cap) {
-                        S.sec_next[j] = sec_head; S.sec_kind[j] = (uint8_t)sbase; S.sec_len[j] = 0; S.sec_read[j] = 0; S.sec_qpos[j] = 0;
-#pragma unroll
-                        for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = sm.sacc[k][tid];
-                        sec_head = j;
-                    }
-                }
-                const int64_t idx = (int64_t)ci.row * S.n_slots + ci.slot0 + tid;
-                const int64_t stride = (int64_t)S.n_rows * S.n_slots;
-                S.ncover[idx] = ncover; S.npass[idx] = npass; S.flags[idx] = (uint8_t)flags; S.pbase[idx] = (uint8_t)pbase;
-                S.sec_head[idx] = sec_head;
-                uint32_t *ps = S.pstats + idx;
-                ps[0 * stride] = acc.count; ps[1 * stride] = acc.mapq; ps[2 * stride] = acc.baseq; ps[3 * stride] = acc.se;
-                ps[4 * stride] = acc.plus; ps[5 * stride] = acc.count - acc.plus; ps[6 * stride] = __float_as_uint(__double2float_rn(acc.posd));
-                ps[7 * stride] = __float_as_uint(acc.nmf); ps[8 * stride] = acc.mmqs; ps[9 * stride] = acc.nq2;
-                ps[10 * stride] = __float_as_uint(acc.q2d); ps[11 * stride] = acc.clip; ps[12 * stride] = __float_as_uint(acc.d3p);
-            }
-        }
+        if (ci.flags & 4u) site_emit(P, sm.sacc, ci, S0);   // last chunk of the tile
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);   // this warp is done with the slot
     }
     // warning counters: warp-reduce then one atomic per warp
+    uint32_t warn_sm = S0.warn_sm, warn_nm = S0.warn_nm;
     for (int o = 16; o; o >>= 1) { warn_sm += __shfl_xor_sync(0xffffffffu, warn_sm, o); warn_nm += __shfl_xor_sync(0xffffffffu, warn_nm, o); }
     if (lane == 0) {
         if (warn_sm) atomicAdd(P.res.warn + 0, (unsigned long long)warn_sm);
