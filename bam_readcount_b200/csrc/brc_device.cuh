@@ -80,7 +80,8 @@ struct RegionDev {
 };
 
 struct RefWin {
-    const char *seq;    // device pointer to 4-bit reference CODES (seq_nt16_table of the FASTA characters), [0] = position win_beg
+    const char *seq;    // device pointer to PACKED 4-bit reference codes (seq_nt16_table of the FASTA characters, two per
+                        // byte, first in the high nibble); symbol 0 = position win_beg; 16 readable bytes of padding
     int64_t chrom_len;
     int64_t win_beg;
     int64_t win_len;

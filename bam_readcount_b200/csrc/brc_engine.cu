@@ -7,6 +7,7 @@
 // in the CUDA kernels of brc_kernels.cu; this file only batches, copies and launches.
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 #include "brc_engine_internal.h"
 
@@ -92,7 +93,8 @@ int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64
     if (!r) { e->refs.emplace_back(); r = &e->refs.back(); }
     r->tid = tid; r->name = contig_name ? contig_name : ""; r->chrom_len = chrom_len; r->win_beg = win_beg; r->win_len = win_len;
     r->seq.assign(seq, (size_t)win_len);
-    CU(r->dev.reserve((size_t)win_len + 16), "cudaMalloc(reference)");
+    CU(r->dev.reserve((size_t)win_len / 2 + 32), "cudaMalloc(reference)");
+    CU(cudaMemsetAsync(r->dev.p, 0xFF, (size_t)win_len / 2 + 32, e->stream), "memset(reference)");
     {   // upload the FASTA characters, keep only their 4-bit codes on the device (K0 compares nibbles)
         DevBuf ascii;
         CU(ascii.reserve((size_t)win_len + 16), "cudaMalloc(reference ascii)");
@@ -113,16 +115,50 @@ int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64
 
 int brc_reset(brc_engine *e) {
     if (!e) return BRC_E_INVALID;
-    e->reads.clear(); e->regions.clear(); e->region_open = false; e->adm.reset(); e->n_indel_ops = 0;
+    e->reads.clear(); e->is_borrowed = false; e->regions.clear(); e->region_open = false; e->adm.reset(); e->n_indel_ops = 0;
     e->results_valid = false; e->planned = false; e->tiles.clear(); e->regions_dev.clear(); e->n_slots = 0;
     for (auto &w : e->warn_counts) w = 0;
     return BRC_OK;
+}
+
+// A borrowed batch becomes an owned copy (bulk memcpy) as soon as anything else is pushed after it.
+static void materialize_borrowed(brc_engine *e) {
+    const brc_read_batch &B = e->borrowed;
+    HostReads &H = e->reads;
+    const size_t n = (size_t)B.n_reads;
+    H.pos.assign(B.pos, B.pos + n); H.flag.assign(B.flag, B.flag + n); H.mapq.assign(B.mapq, B.mapq + n);
+    if (B.lib) H.lib.assign(B.lib, B.lib + n); else H.lib.assign(n, 0);
+    H.l_qseq.assign(B.l_qseq, B.l_qseq + n); H.nm.assign(B.nm, B.nm + n); H.sm.assign(B.sm, B.sm + n);
+    H.region.assign(n, 0);
+    // offsets are rebased to 0 (a borrowed batch may be a slice of larger pools)
+    const uint64_t c0 = B.cigar_off[0], s0 = B.seq_off[0], q0 = B.qual_off[0];
+    H.cigar_off.resize(n + 1); H.seq_off.resize(n + 1); H.qual_off.resize(n + 1);
+    for (size_t i = 0; i <= n; ++i) { H.cigar_off[i] = B.cigar_off[i] - c0; H.seq_off[i] = B.seq_off[i] - s0; H.qual_off[i] = B.qual_off[i] - q0; }
+    H.cigar.assign(B.cigar + c0, B.cigar + B.cigar_off[n]);
+    H.seq.assign(B.seq + s0, B.seq + B.seq_off[n]);
+    H.qual.assign(B.qual + q0, B.qual + B.qual_off[n]);
+    e->is_borrowed = false;
+    if (e->region_open && n) {   // more reads may follow in the same region: rebuild the pileup-buffer admission state
+        Admission &A = e->adm;
+        A.reset();
+        A.max_tid = A.it_tid = e->regions.back().tid; A.max_pos = A.it_pos = H.pos[n - 1];
+        for (size_t i = 0; i < n; ++i) {
+            int64_t l = 0;
+            for (uint64_t k = H.cigar_off[i]; k < H.cigar_off[i + 1]; ++k) {
+                const uint32_t op = H.cigar[k] & 0xF;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) l += H.cigar[k] >> 4;
+            }
+            const int64_t end = H.cigar_off[i + 1] > H.cigar_off[i] ? (int64_t)H.pos[i] + l : (int64_t)H.pos[i] + 1;
+            if (end >= A.it_pos) A.live_ends.push(end);
+        }
+    }
 }
 
 int brc_begin_region(brc_engine *e, int32_t tid, int32_t beg, int32_t end, int32_t site_list_mode) {
     if (!e || e->region_open) return set_error(e, BRC_E_INVALID, "begin_region: previous region still open");
     brc_region r{};
     r.tid = tid; r.beg = beg; r.end = end; r.site_list_mode = site_list_mode;
+    if (e->is_borrowed) materialize_borrowed(e);   // more regions follow: fall back to the engine-owned staging copy
     r.read_lo = r.read_hi = e->reads.n();
     r.first_pos = beg - 1 > 0 ? beg - 1 : 0;
     r.slot_base = e->regions.empty() ? 0 : e->regions.back().slot_base + e->regions.back().n_slots;
@@ -147,6 +183,7 @@ int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_
                   int32_t nm, int32_t sm, uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq,
                   const uint8_t *qual) {
     if (!e || !e->region_open) return set_error(e, BRC_E_INVALID, "push_read: no open region");
+    if (e->is_borrowed) materialize_borrowed(e);
     if (l_qseq < 0 || (n_cigar && !cigar) || (l_qseq && (!seq || !qual))) return set_error(e, BRC_E_INVALID, "push_read: null data");
     brc_region &rg = e->regions.back();
     Admission &A = e->adm;
@@ -182,10 +219,63 @@ int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_
     return BRC_OK;
 }
 
+// Parallel scan of a batch: are all reads admitted by the pileup buffer as they are (so the batch can be used in
+// place), and what is the largest bam_endpos?  The -d rule cannot fire when the whole batch is smaller than max_cnt.
+struct BatchScan { bool ok = true; int64_t max_end = 0; int64_t indel_ops = 0; };
+static BatchScan scan_batch(const brc_read_batch *b, int32_t rtid, int per_lib, int n_rows) {
+    const int64_t n = b->n_reads;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(hw ? hw : 1), (int64_t)16, n / 65536 + 1}));
+    std::vector<BatchScan> part((size_t)nt);
+    auto work = [&](int t) {
+        const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        BatchScan r;
+        for (int64_t i = lo; i < hi && r.ok; ++i) {
+            if ((b->tid && b->tid[i] != rtid) || (b->flag[i] & 4)) { r.ok = false; break; }
+            if (i > 0 && b->pos[i] < b->pos[i - 1]) { r.ok = false; break; }
+            if (per_lib && b->lib && b->lib[i] != BRC_LIB_NONE && (int)b->lib[i] >= n_rows) { r.ok = false; break; }
+            const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
+            int64_t l = 0;
+            for (uint64_t k = c0; k < c1; ++k) {
+                const uint32_t op = b->cigar[k] & 0xF;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) l += b->cigar[k] >> 4;
+                if (op == 1 || op == 2) ++r.indel_ops;
+            }
+            const int64_t end = c1 > c0 ? (int64_t)b->pos[i] + l : (int64_t)b->pos[i] + 1;
+            if (end <= (int64_t)b->pos[i] && i > 0 && b->pos[i] == b->pos[i - 1]) { r.ok = false; break; }  // zero-span read: exact linking rule lives in brc_push_read
+            if (end > r.max_end) r.max_end = end;
+        }
+        part[(size_t)t] = r;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    BatchScan out;
+    for (auto &r : part) { out.ok = out.ok && r.ok; out.max_end = std::max(out.max_end, r.max_end); out.indel_ops += r.indel_ops; }
+    return out;
+}
+
 int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
     if (!e || !b) return BRC_E_INVALID;
     if (!e->region_open) return set_error(e, BRC_E_INVALID, "push_reads: no open region");
-    const int32_t rtid = e->regions.back().tid;
+    if (e->is_borrowed) materialize_borrowed(e);
+    brc_region &rg = e->regions.back();
+    const int32_t rtid = rg.tid;
+    // Fast path: the first batch after brc_reset, pushed into the only region, with every record admitted as is
+    // (mapped, on the region's contig, sorted, and fewer records than -d so the max-count rule cannot fire):
+    // keep a VIEW of the caller's arrays — brc_compute DMAs straight out of them (pin them for full PCIe speed).
+    if (e->regions.size() == 1 && e->reads.n() == 0 && b->n_reads > 0 && b->n_reads < (int64_t)e->cfg.max_cnt &&
+        b->n_reads < 0x7fffffffLL && e->adm.max_pos < 0) {
+        const BatchScan sc = scan_batch(b, rtid, e->cfg.per_lib, e->n_rows);
+        if (sc.ok) {
+            e->is_borrowed = true; e->borrowed = *b;
+            e->n_indel_ops += sc.indel_ops;
+            if (sc.max_end > e->open_max_end) e->open_max_end = sc.max_end;
+            rg.read_hi = b->n_reads;
+            return BRC_OK;
+        }
+    }
     for (int64_t i = 0; i < b->n_reads; ++i) {
         const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
         int rc = brc_push_read(e, b->tid ? b->tid[i] : rtid, b->pos[i], b->flag[i], b->mapq[i], b->lib ? b->lib[i] : (uint16_t)0,
@@ -373,13 +463,16 @@ int brc_compute(brc_engine *e) {
     int rc = build_geometry(e, e->regions.data(), (int64_t)e->regions.size());
     if (rc != BRC_OK) return rc;
     HostReads &H = e->reads;
-    const int64_t n = H.n();
+    const bool bw = e->is_borrowed;
+    const brc_read_batch &B = e->borrowed;
+    const int64_t n = e->n_host_reads();
+    const int32_t *h_pos = bw ? B.pos : H.pos.data();
     // reference window must cover every read's span (K0 reads it; the emitter reads deletion alleles)
     for (const brc_region &r : e->regions) {
         const HostRef *hr = find_ref(e, r.tid);
         if (!hr) return set_error(e, BRC_E_NO_REFERENCE, "no reference for contig");
         if (r.read_hi > r.read_lo) {
-            int64_t lo = H.pos[(size_t)r.read_lo], hi = (int64_t)r.first_pos + r.n_slots;
+            int64_t lo = h_pos[(size_t)r.read_lo], hi = (int64_t)r.first_pos + r.n_slots;
             lo = std::max<int64_t>(0, std::min<int64_t>(lo, r.first_pos));
             hi = std::min(hi, hr->chrom_len);
             if (lo < hr->win_beg || hi > hr->win_beg + hr->win_len)
@@ -389,13 +482,22 @@ int brc_compute(brc_engine *e) {
     rc = alloc_outputs(e, n);
     if (rc != BRC_OK) return rc;
     cudaStream_t s = e->stream;
-    // H2D of the read arrays
-    const void *src[14] = {H.pos.data(), H.flag.data(), H.mapq.data(), H.lib.data(), H.l_qseq.data(), H.nm.data(), H.sm.data(),
-                           H.cigar_off.data(), H.cigar.data(), H.seq_off.data(), H.seq.data(), H.qual_off.data(), H.qual.data(),
-                           H.region.data()};
+    // H2D of the read arrays (borrowed batches: straight from the caller's buffers)
+    std::vector<uint16_t> zero_lib;
+    const uint16_t *h_lib = bw ? B.lib : H.lib.data();
+    if (bw && !B.lib) { zero_lib.assign((size_t)n, 0); h_lib = zero_lib.data(); }
+    const uint64_t n_cig = bw ? B.cigar_off[n] : (uint64_t)H.cigar.size();
+    const uint64_t n_seq = bw ? B.seq_off[n] : (uint64_t)H.seq.size();
+    const uint64_t n_qual = bw ? B.qual_off[n] : (uint64_t)H.qual.size();
+    const void *src[14] = {h_pos, bw ? (const void *)B.flag : H.flag.data(), bw ? (const void *)B.mapq : H.mapq.data(), h_lib,
+                           bw ? (const void *)B.l_qseq : H.l_qseq.data(), bw ? (const void *)B.nm : H.nm.data(),
+                           bw ? (const void *)B.sm : H.sm.data(), bw ? (const void *)B.cigar_off : H.cigar_off.data(),
+                           bw ? (const void *)B.cigar : H.cigar.data(), bw ? (const void *)B.seq_off : H.seq_off.data(),
+                           bw ? (const void *)B.seq : H.seq.data(), bw ? (const void *)B.qual_off : H.qual_off.data(),
+                           bw ? (const void *)B.qual : H.qual.data(), bw ? nullptr : (const void *)H.region.data()};
     const size_t bytes[14] = {(size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 2, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
-                              (size_t)(n + 1) * 8, H.cigar.size() * 4, (size_t)(n + 1) * 8, H.seq.size(), (size_t)(n + 1) * 8,
-                              H.qual.size(), (size_t)n * 4};
+                              (size_t)(n + 1) * 8, (size_t)n_cig * 4, (size_t)(n + 1) * 8, (size_t)n_seq, (size_t)(n + 1) * 8,
+                              (size_t)n_qual, bw ? (size_t)0 : (size_t)n * 4};
     for (int k = 0; k < 14; ++k) {
         CU(e->d_in[k].reserve(bytes[k] + 16), "cudaMalloc(reads)");
         if (bytes[k]) CU(cudaMemcpyAsync(e->d_in[k].p, src[k], bytes[k], cudaMemcpyHostToDevice, s), "H2D reads");

@@ -81,8 +81,14 @@ struct brc_engine {
     std::vector<brc::HostRef> refs;
     brc::DevBuf d_refs;              // RefWin table
 
-    // push path
+    // push path.  `reads` = engine-owned staging copy; `borrowed` = zero-copy view of the caller's batch
+    // (one fully-admitted brc_push_reads per brc_reset): H2D copies then run straight from the caller's buffers.
     brc::HostReads reads;
+    bool is_borrowed = false;
+    brc_read_batch borrowed{};
+    int64_t n_host_reads() const { return is_borrowed ? borrowed.n_reads : reads.n(); }
+    const uint8_t *host_seq() const { return is_borrowed ? borrowed.seq : reads.seq.data(); }
+    const uint64_t *host_seq_off() const { return is_borrowed ? borrowed.seq_off : reads.seq_off.data(); }
     std::vector<brc_region> regions;
     bool region_open = false;
     brc::Admission adm;

@@ -69,7 +69,7 @@ void format_region(const brc_engine *e, int64_t g, const char *const *lib_names,
     const int64_t *sread = e->h_sec_read.as<int64_t>();
     const uint32_t *sstats = e->h_sec_stats.as<uint32_t>();
     const int64_t SC = e->h_sec_cap;
-    const brc::HostReads &H = e->reads;
+    const uint8_t *h_seq = e->host_seq(); const uint64_t *h_seq_off = e->host_seq_off();
     std::string rec;
     struct Indel { std::string allele; Stat st; };
     std::vector<Indel> indels;
@@ -95,7 +95,7 @@ void format_region(const brc_engine *e, int64_t g, const char *const *lib_names,
                 Indel in; in.st = t;
                 if (skind[j] == BRC_KIND_INS) {          // "+" + canonicalised read bases qpos+1..qpos+len  (R:...:324-330)
                     in.allele = "+";
-                    const uint8_t *sq = H.seq.data() + H.seq_off[(size_t)sread[j]];
+                    const uint8_t *sq = h_seq + h_seq_off[(size_t)sread[j]];
                     for (int k = 1; k <= slen[j]; ++k) { int i = sqpos[j] + k; uint8_t b = sq[i >> 1]; in.allele += kNt[kCanon[(i & 1) ? (b & 15) : (b >> 4)]]; }
                 } else {                                 // "-" + raw reference characters pos+1..pos+len (R:...:331-339)
                     in.allele = "-";
@@ -142,7 +142,7 @@ void format_region(const brc_engine *e, int64_t g, const char *const *lib_names,
 extern "C" int64_t brc_format_text(brc_engine *e, int64_t region_index, const char *const *lib_names, char *buf, int64_t cap) {
     if (!e) return BRC_E_INVALID;
     if (!e->results_valid) return brc::set_error(e, BRC_E_INVALID, "format_text: no results");
-    if (e->reads.n() == 0 && e->h_n_sec > 0) return brc::set_error(e, BRC_E_INVALID, "format_text: needs the pushed reads (push path only)");
+    if (e->n_host_reads() == 0 && e->h_n_sec > 0) return brc::set_error(e, BRC_E_INVALID, "format_text: needs the pushed reads (push path only)");
     if (region_index >= (int64_t)e->regions.size()) return BRC_E_INVALID;
     std::string out;
     EmitState st(e->n_rows);

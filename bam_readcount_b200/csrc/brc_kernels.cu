@@ -72,9 +72,13 @@ cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tile
 // ---------------------------------------------------------------------------------------------
 // reference window: ASCII -> 4-bit codes, once per brc_set_reference (part of load_reference, not of a step)
 // ---------------------------------------------------------------------------------------------
-__global__ void ref_encode_kernel(const char *ascii, uint8_t *code, int64_t n) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) code[i] = c_nt16[(unsigned char)ascii[i]];
+__global__ void ref_encode_kernel(const char *ascii, uint8_t *packed, int64_t n) {
+    // two bases per byte, first base in the high nibble (the BAM sequence packing), so K0 can XOR 8 bases at a time
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (2 * b >= n) return;
+    const uint32_t hi = c_nt16[(unsigned char)ascii[2 * b]];
+    const uint32_t lo = (2 * b + 1 < n) ? c_nt16[(unsigned char)ascii[2 * b + 1]] : 15u;
+    packed[b] = (uint8_t)((hi << 4) | lo);
 }
 
 static cudaError_t ensure_tables() {
@@ -92,7 +96,8 @@ static cudaError_t ensure_tables() {
 cudaError_t launch_ref_encode(const char *d_ascii, uint8_t *d_code, int64_t n, cudaStream_t s) {
     cudaError_t e = ensure_tables();
     if (e != cudaSuccess || n == 0) return e;
-    ref_encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_ascii, d_code, n);
+    const int64_t nb = (n + 1) / 2;
+    ref_encode_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(d_ascii, d_code, n);
     return cudaGetLastError();
 }
 
@@ -143,6 +148,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // then one thread walks one read.  Reference codes come straight from global memory: reads are
 // position-sorted, so a warp's 32 walks touch one or two 128-byte lines per step.
 // ---------------------------------------------------------------------------------------------
+// 8 consecutive 4-bit symbols starting at symbol index t of a packed array (first symbol in the high nibble of a
+// byte), returned big-endian: symbol t in bits 31:28.  Reads up to 8 bytes from the aligned word holding byte t/2.
+__device__ __forceinline__ uint32_t nib8(const uint8_t *base, int64_t t) {
+    const uint8_t *p = base + (t >> 1);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p - sh);
+    const uint32_t w0 = w[0], w1 = w[1];
+    const uint32_t sel = (sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12);
+    uint32_t x = __byte_perm(w0, w1, sel);                       // bytes p[0..3], p[0] in the most significant byte
+    if (t & 1) x = (x << 4) | ((__byte_perm(w0, w1, sh + 4u) >> 4) & 0xFu);
+    return x;
+}
+__device__ __forceinline__ uint32_t nib_nonzero(uint32_t v) { return (v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x11111111u; }
+
 constexpr int K0_READS = 128;
 constexpr int K0_SEQ_CAP = K0_READS * 80 + 32;
 constexpr int K0_QUAL_CAP = K0_READS * 160 + 32;
@@ -192,7 +211,7 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     // generic pointers: shared memory when staged, the global pools otherwise (reads too long for the stage)
     const uint8_t *seq = staged ? (ks.seq + (soff - sa)) : (R.seq + soff);
     const uint8_t *qual = staged ? (ks.qual + (qoffb - qa)) : (R.qual + qoffb);
-    const uint8_t *refc = reinterpret_cast<const uint8_t *>(rw.seq);   // 4-bit codes (launch_ref_encode)
+    const uint8_t *refc = reinterpret_cast<const uint8_t *>(rw.seq);   // packed 4-bit codes (launch_ref_encode)
 
     // --- fetch_func CIGAR/reference walk (R:...:133-199) + bam_cigar2rlen + SIMPLE detection ---
     uint32_t sum_mmq = 0;
@@ -220,14 +239,24 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
                 if (rg.ref_len_check && reference_position > rw.chrom_len) jn = 0;   // -l mode: every position is skipped (R:...:144-148)
                 else { const int64_t room = rw.chrom_len - reference_position; jn = room > 0 ? (int)room : 0; hit_nul = true; }
             }
+            // compare 8 bases per step: XOR of the packed read nibbles with the packed reference codes.
+            // Positions outside the supplied reference window count as 'N' (no mismatch): clip to the window.
             const int64_t wrel = reference_position - rw.win_beg;
-            for (int j = 0; j < jn; ++j) {
-                const int cur = read_position + j;
-                const int64_t w = wrel + j;
-                const uint32_t ref_base = (w >= 0 && w < rw.win_len) ? refc[w] : 15u;   // outside the supplied window: 'N'
-                const uint32_t b = seq[cur >> 1];
-                const uint32_t read_base = (cur & 1) ? (b & 0xFu) : (b >> 4);
-                if (read_base != ref_base && ref_base != 15u && read_base != 0u) {
+            int j = wrel < 0 ? (int)min((int64_t)jn, -wrel) : 0;
+            const int jend = (int)max((int64_t)j, min((int64_t)jn, rw.win_len - wrel));
+            for (; j < jend; j += 8) {
+                const uint32_t X = nib8(seq, read_position + j);
+                const uint32_t Y = nib8(refc, wrel + j);
+                const uint32_t x = X ^ Y;
+                if (x == 0u) continue;
+                const int nv = jend - j;
+                const uint32_t keep = nv >= 8 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (4 * nv));
+                // mismatch iff read != ref && ref != 15 && read != 0   (R:...:152)
+                uint32_t m = nib_nonzero(x) & ~((Y & (Y >> 1) & (Y >> 2) & (Y >> 3)) & 0x11111111u) & nib_nonzero(X) & keep;
+                while (m) {
+                    const int k8 = __clz(m) >> 2;          // flag of symbol i sits at bit 28-4i
+                    m &= ~(0x10000000u >> (4 * k8));
+                    const int cur = read_position + j + k8;
                     const int q = qual[cur];
                     if (last_mm_pos != -1) {
                         if (last_mm_pos + 1 != cur) { sum_mmq += (uint32_t)last_mm_qual; last_mm_qual = q; }

