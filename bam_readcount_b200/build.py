@@ -42,7 +42,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(HERE, "..", "include"), "-o", LIB] + \
+    extra = os.environ.get("BRC_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-I", os.path.join(HERE, "..", "include"), "-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or p.returncode != 0:

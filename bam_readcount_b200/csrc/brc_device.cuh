@@ -61,8 +61,8 @@ static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
 
 // K1 shared-memory staging: capacity of ONE slot of the 2-stage TMA ring
 constexpr int STAGE_READS = 96;                 // descriptors per chunk
-constexpr int STAGE_QUAL = 12288 + 32;          // staged quality bytes per chunk (incl. 16-B alignment slack both ends)
-constexpr int STAGE_SEQ = 6144 + 32;            // staged packed-base bytes per chunk
+constexpr int STAGE_QUAL = 96 * 152 + 32;          // staged quality bytes per chunk (incl. 16-B alignment slack both ends)
+constexpr int STAGE_SEQ = 96 * 76 + 32;            // staged packed-base bytes per chunk
 
 struct TileInfo {
     int32_t pos0;       // absolute position of the tile's first site

@@ -124,6 +124,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 // producer-side wait: long suspend-time hint so the idle producer lane does not burn issue slots
+template <uint32_t HINT_NS>
+__device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITH_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONEH_%=;\n"
+        "bra WAITH_%=;\n"
+        "DONEH_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(HINT_NS) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t phase) {
     asm volatile(
         "{\n"
@@ -214,6 +226,8 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     const uint8_t *refc = reinterpret_cast<const uint8_t *>(rw.seq);   // packed 4-bit codes (launch_ref_encode)
 
     // --- fetch_func CIGAR/reference walk (R:...:133-199) + bam_cigar2rlen + SIMPLE detection ---
+    // Flattened into ONE loop whose iterations are either "fetch the next CIGAR op" or "compare 8 bases of the
+    // current M op", so the 32 reads of a warp stay converged whatever their CIGAR shapes are.
     uint32_t sum_mmq = 0;
     int left_clip = 0, clipped_length = l_qseq, right_clip = l_qseq;
     int last_mm_pos = -1, last_mm_qual = 0;
@@ -223,32 +237,49 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     int64_t rlen = 0;               // reference span (all ref-consuming ops, incl. = and X)
     int n_refops = 0, qoff = 0;
     bool simple = true, seen_ref = false;
-    for (uint32_t k = 0; k < n_cigar; ++k) {
-        const uint32_t c = cig[k];
-        const int op_length = (int)(c >> 4);
-        const uint32_t op = c & 0xFu;
-        if (is_refop(op)) { rlen += op_length; n_refops++; seen_ref = true; if (!is_matchop(op)) simple = false; }
-        else if (op == 1 || op == 6) simple = false;
-        else if (op == 4 && !seen_ref) qoff += op_length;
-        if (!walking) continue;
-        if (op == 0) {
-            // positions whose reference base exists: [0, jn); at refpos == chrom_len the reference string's NUL stops the walk
-            int jn = op_length;
-            bool hit_nul = false;
-            if (reference_position + op_length > rw.chrom_len) {
-                if (rg.ref_len_check && reference_position > rw.chrom_len) jn = 0;   // -l mode: every position is skipped (R:...:144-148)
-                else { const int64_t room = rw.chrom_len - reference_position; jn = room > 0 ? (int)room : 0; hit_nul = true; }
+    uint32_t k = 0;
+    bool in_m = false, hit_nul = false;
+    int j = 0, jend = 0, m_len = 0;
+    int64_t wrel = 0;
+    for (;;) {
+        if (!in_m) {
+            if (k >= n_cigar) break;
+            const uint32_t c = cig[k];
+            const int op_length = (int)(c >> 4);
+            const uint32_t op = c & 0xFu;
+            if (is_refop(op)) { rlen += op_length; n_refops++; seen_ref = true; if (!is_matchop(op)) simple = false; }
+            else if (op == 1 || op == 6) simple = false;
+            else if (op == 4 && !seen_ref) qoff += op_length;
+            if (walking) {
+                if (op == 0) {
+                    // positions whose reference base exists: [0, jn); at refpos == chrom_len the reference string's NUL stops the walk
+                    int jn = op_length;
+                    hit_nul = false;
+                    if (reference_position + op_length > rw.chrom_len) {
+                        if (rg.ref_len_check && reference_position > rw.chrom_len) jn = 0;   // -l mode: every position is skipped (R:...:144-148)
+                        else { const int64_t room = rw.chrom_len - reference_position; jn = room > 0 ? (int)room : 0; hit_nul = true; }
+                    }
+                    // positions outside the supplied reference window count as 'N' (no mismatch): clip to the window
+                    wrel = reference_position - rw.win_beg;
+                    j = wrel < 0 ? (int)min((int64_t)jn, -wrel) : 0;
+                    jend = (int)max((int64_t)j, min((int64_t)jn, rw.win_len - wrel));
+                    m_len = op_length; in_m = true;
+                } else if (op == 2 || op == 3) reference_position += op_length;
+                else if (op == 1) read_position += op_length;
+                else if (op == 4) {
+                    read_position += op_length; clipped_length -= op_length;
+                    if (k == 0) left_clip += op_length; else right_clip -= op_length;
+                }
             }
-            // compare 8 bases per step: XOR of the packed read nibbles with the packed reference codes.
-            // Positions outside the supplied reference window count as 'N' (no mismatch): clip to the window.
-            const int64_t wrel = reference_position - rw.win_beg;
-            int j = wrel < 0 ? (int)min((int64_t)jn, -wrel) : 0;
-            const int jend = (int)max((int64_t)j, min((int64_t)jn, rw.win_len - wrel));
-            for (; j < jend; j += 8) {
-                const uint32_t X = nib8(seq, read_position + j);
-                const uint32_t Y = nib8(refc, wrel + j);
-                const uint32_t x = X ^ Y;
-                if (x == 0u) continue;
+            ++k;
+            continue;
+        }
+        if (j < jend) {
+            // 8 bases per step: XOR of the packed read nibbles with the packed reference codes
+            const uint32_t X = nib8(seq, read_position + j);
+            const uint32_t Y = nib8(refc, wrel + j);
+            const uint32_t x = X ^ Y;
+            if (x != 0u) {
                 const int nv = jend - j;
                 const uint32_t keep = nv >= 8 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> (4 * nv));
                 // mismatch iff read != ref && ref != 15 && read != 0   (R:...:152)
@@ -265,15 +296,13 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
                     } else { last_mm_pos = cur; last_mm_qual = q; }
                 }
             }
-            // site-list mode skips positions beyond chrom_len (R:...:144-148) but position == chrom_len still reads the NUL
-            if (hit_nul) { walking = false; continue; }
-            reference_position += op_length; read_position += op_length;
-        } else if (op == 2 || op == 3) reference_position += op_length;
-        else if (op == 1) read_position += op_length;
-        else if (op == 4) {
-            read_position += op_length; clipped_length -= op_length;
-            if (k == 0) left_clip += op_length; else right_clip -= op_length;
+            j += 8;
+            continue;
         }
+        // M op finished.  Site-list mode skips positions beyond chrom_len (R:...:144-148) but position == chrom_len still reads the NUL.
+        if (hit_nul) walking = false;
+        else { reference_position += m_len; read_position += m_len; }
+        in_m = false;
     }
     sum_mmq += (uint32_t)last_mm_qual;
     if (n_refops != 1) simple = false;
@@ -352,9 +381,15 @@ cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s) {
 // reads in file order and accumulates in registers.  full/empty mbarriers are the only
 // synchronisation, so chunk i+1 is in flight while chunk i is being consumed.
 // ---------------------------------------------------------------------------------------------
+#ifdef BRC_K1_PROFILE
+__device__ unsigned long long g_k1prof[8];   // [0] consumer wait, [1] consumer busy, [2] producer wait-empty, [3] producer issue, [4] items
+#endif
 constexpr int N_CONSUMER_WARPS = TILE / 32;
 constexpr int K1_THREADS = TILE + 32;
 constexpr int NSTAGE = 2;
+#ifndef BRC_K1_CTAS_PER_SM
+#define BRC_K1_CTAS_PER_SM 3
+#endif
 
 struct Acc {  // 13 accumulators in registers (print order BRC_S_*); minus strand = count - plus
     uint32_t count, mapq, baseq, se, plus;
@@ -506,42 +541,66 @@ struct __align__(128) PileupSmem {
     uint64_t full[NSTAGE], empty[NSTAGE];
 };
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // per-thread (= per-site) state of a consumer, all in registers
 struct SiteState {
     Acc acc;
     uint32_t ncover, npass, flags, pbase, sbase;
     int32_t sec_head;
     uint32_t warn_sm = 0, warn_nm = 0;
-    bool active, warp_done;
-    int32_t site, wfirst, wlast;
-    int tid, warp0;
+    bool warp_done;
+    int32_t site;      // -1 for lanes beyond the tile's last site (never covered: positions are >= 0)
+    int32_t wfirst;    // first site of this warp; the warp's window is [wfirst, wfirst+31]
 };
-__device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci) {
+__device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci, int tid) {
     Acc &a = S.acc;
     a.count = a.mapq = a.baseq = a.se = a.plus = a.mmqs = a.nq2 = a.clip = 0;
     a.nmf = a.q2d = a.d3p = 0.0f; a.posd = 0.0;
     S.ncover = S.npass = S.flags = 0; S.pbase = S.sbase = NO_BASE; S.sec_head = -1;
-    S.active = S.tid < ci.n; S.site = ci.pos0 + S.tid;
-    S.wfirst = ci.pos0 + S.warp0; S.wlast = ci.pos0 + min(S.warp0 + 31, ci.n - 1);
-    S.warp_done = S.warp0 >= ci.n;
+    S.site = tid < ci.n ? ci.pos0 + tid : -1;
+    S.wfirst = ci.pos0 + (tid & ~31);
+    S.warp_done = (tid & ~31) >= ci.n;
 }
+
+__device__ __forceinline__ int2 lds_i2(const void *p) { return *reinterpret_cast<const int2 *>(p); }
 
 // The hot loop: one warp walks the chunk's reads in file order; lane = site.
 template <bool PER_LIB, bool STAGED>
 __device__ __forceinline__ void process_chunk(const PileupParams &P, const StageBuf &sb, uint32_t (*sacc)[TILE], const ChunkInfo &ci,
-                                              SiteState &S) {
-    const int n_in = ci.r1 - ci.r0;
+                                              SiteState &S, int tid) {
     const int4 *ds = sb.desc;
-    const uint8_t *qual_s = sb.qual - ci.qbase32;   // staged bytes are addressed with the reads' low-32 pool offsets
-    const uint8_t *seq_s = sb.seq - ci.sbase32;
-    const int tid = S.tid;
-    for (int i = 0; i < n_in; ++i, ds += 5) {
-        const int4 q0 = ds[0];                                   // pos,end,fm,lib_nc
-        if (q0.x > S.wlast) { S.warp_done = true; break; }       // reads are position-sorted within a region
-        if (q0.y <= S.wfirst) continue;
-        const bool cover = S.active && S.site >= q0.x && S.site < q0.y;
+    const int4 *const ds_end = ds + (ci.r1 - ci.r0) * 5;
+    const uint32_t qual_s = smem_u32(sb.qual) - ci.qbase32;   // staged bytes are addressed with the reads' low-32 pool offsets
+    const uint32_t seq_s = smem_u32(sb.seq) - ci.sbase32;
+    const int32_t wfirst = S.wfirst, wlast = S.wfirst + 31;
+    {   // vectorised skip of the leading reads that end before this warp's first site (32 reads per ballot):
+        // keeps the 8 warps of a tile in step — the last warp would otherwise walk ~45 dead reads one by one
+        const int n_in = ci.r1 - ci.r0, lane = tid & 31;
+        int start = 0;
+        for (; start < n_in; start += 32) {
+            const int j = start + lane;
+            const int endj = j < n_in ? ds[j * 5].y : 0x7fffffff;
+            const unsigned m = __ballot_sync(0xffffffffu, endj > wfirst);
+            if (m) { start += __ffs(m) - 1; break; }
+        }
+        if (start >= n_in) return;
+        ds += start * 5;
+    }
+    int2 pe_next = lds_i2(ds);                                    // software prefetch of the next read's (pos,end)
+    for (; ds < ds_end; ds += 5) {
+        const int2 pe = pe_next;
+        pe_next = lds_i2(ds + 5);                                 // may run one record past the chunk: staged garbage, never used
+        if (pe.x > wlast) { S.warp_done = true; break; }          // reads are position-sorted within a region
+        if (pe.y <= wfirst) continue;
+        const bool cover = S.site >= pe.x && S.site < pe.y;
+        const int2 fl2 = lds_i2(&ds[0].z);                        // fm, lib_nc
         if (PER_LIB) {
-            const uint32_t lib = (uint32_t)q0.w & 0xFFFFu;
+            const uint32_t lib = (uint32_t)fl2.y & 0xFFFFu;
             if (lib == LIB_NONE) { if (cover) S.flags |= 1u; continue; }
             if (lib != ci.row) continue;
             // -p: pileup_func returns at the first read without a library (R:...:281-284); nothing after
@@ -550,38 +609,38 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         }
         if (!cover) continue;
         S.ncover++;
-        const uint32_t fm = (uint32_t)q0.z;
+        const uint32_t fm = (uint32_t)fl2.x;
         const int4 q3 = ds[3];                                   // qual32,seq32,cig,n_cigar
         int qpos, indel = 0;
-        if (fm & FM_SIMPLE) qpos = S.site - q0.x + q3.z;
+        if (fm & FM_SIMPLE) qpos = S.site - pe.x + q3.z;
         else {
-            const int3 rr = resolve_general(P.cigar + (uint32_t)q3.z, (uint32_t)q3.w, q0.x, S.site);
+            const int3 rr = resolve_general(P.cigar + (uint32_t)q3.z, (uint32_t)q3.w, pe.x, S.site);
             if (rr.z) continue;                                  // is_del
             qpos = rr.x; indel = rr.y;
         }
         const uint32_t mapq = (fm >> 16) & 0xFFu;
         if ((int)mapq < P.min_mapq) continue;
-        const int32_t r = ci.r0 + i;
         uint32_t bq;
-        if (STAGED) bq = qual_s[(uint32_t)q3.x + (uint32_t)qpos];
-        else bq = P.qual[P.qual_off[r] + (uint32_t)qpos];
+        if (STAGED) bq = lds_u8(qual_s + (uint32_t)q3.x + (uint32_t)qpos);
+        else bq = P.qual[P.qual_off[ci.r0 + (int)((ds - sb.desc) / 5)] + (uint32_t)qpos];
         if ((int)bq < P.min_bq) continue;
         if (fm & FLAG_FILTER) continue;
         S.npass++;
-        const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // rare: a tag the reference warns about is missing
+        const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // a tag the reference warns about is missing
         if (indel != 0) {
+            const int32_t r = ci.r0 + (int)((ds - sb.desc) / 5);
             S.sec_head = rare_event(P, S.sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
-            if (warns) { S.warn_nm += (fm & FM_NM_ABSENT) ? 1u : 0u; S.warn_sm += (fm & FM_SM_MISSING) ? 1u : 0u; }
+            if (warns) { S.warn_nm += (fm >> 25) & 1u; S.warn_sm += (fm >> 26) & 1u; }
             if (indel > 0 && P.insertion_centric) continue;
         }
-        if (warns) { S.warn_nm += (fm & FM_NM_ABSENT) ? 1u : 0u; S.warn_sm += (fm & FM_SM_MISSING) ? 1u : 0u; }
+        if (warns) { S.warn_nm += (fm >> 25) & 1u; S.warn_sm += (fm >> 26) & 1u; }
         uint32_t byte;
-        if (STAGED) byte = seq_s[(uint32_t)q3.y + ((uint32_t)qpos >> 1)];
-        else byte = P.seq[P.seq_off[r] + ((uint32_t)qpos >> 1)];
+        if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
+        else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
         const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
         if (S.pbase == NO_BASE) S.pbase = base;
         if (base != S.pbase && S.sbase != NO_BASE && base != S.sbase) {   // third base class at this site: rare
-            S.sec_head = rare_event(P, S.sec_head, (int)base, 0, r, qpos, bq, false);
+            S.sec_head = rare_event(P, S.sec_head, (int)base, 0, ci.r0 + (int)((ds - sb.desc) / 5), qpos, bq, false);
             continue;
         }
         const int4 q1 = ds[1];                                   // mmq,clen,lclip,tpi
@@ -621,10 +680,9 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
 }
 
 // last chunk of a tile: write the site's header + primary accumulators (coalesced SoA stores)
-__device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc)[TILE], const ChunkInfo &ci, SiteState &S) {
-    if (!S.active) return;
+__device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc)[TILE], const ChunkInfo &ci, SiteState &S, int tid) {
+    if (tid >= ci.n) return;
     const ResultsDev &R = P.res;
-    const int tid = S.tid;
     int32_t sec_head = S.sec_head;
     if (S.sbase != NO_BASE) {   // move the second base class into the record pool
         const int32_t j = atomicAdd(R.sec_count, 1);
@@ -648,7 +706,7 @@ __device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc
 }
 
 template <bool PER_LIB>
-__global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
+__global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(PileupParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     PileupSmem &sm = *reinterpret_cast<PileupSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -677,7 +735,13 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
             bool first = true;
             do {
                 const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
+#ifdef BRC_K1_PROFILE
+                const long long tp0 = clock64();
+#endif
                 mbar_wait_relaxed(&sm.empty[s], ph ^ 1u);  // consumers released this slot
+#ifdef BRC_K1_PROFILE
+                const long long tp1 = clock64();
+#endif
                 ChunkInfo ci{};
                 ci.work = done ? -1 : (int32_t)w;
                 ci.pos0 = ti.pos0; ci.n = ti.n; ci.slot0 = ti.slot0; ci.row = row;
@@ -686,12 +750,14 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
                 if (r0 < hi) {
                     r1 = min(r0 + STAGE_READS, hi);
                     uint64_t qa, qb, sa, sb; bool staged;
-                    for (;;) {   // as many reads as fit the stage
+                    for (;;) {   // as many reads as fit the stage: shrink proportionally to the overshoot
                         qa = P.qual_off[r0] & ~15ull; qb = (P.qual_off[r1] + 15ull) & ~15ull;
                         sa = P.seq_off[r0] & ~15ull;  sb = (P.seq_off[r1] + 15ull) & ~15ull;
                         staged = (qb - qa) <= (uint64_t)STAGE_QUAL && (sb - sa) <= (uint64_t)STAGE_SEQ;
                         if (staged || r1 - r0 == 1) break;
-                        r1 = r0 + (r1 - r0) / 2;
+                        const double fq = (double)(STAGE_QUAL - 32) / (double)(qb - qa), fs = (double)(STAGE_SEQ - 32) / (double)(sb - sa);
+                        const int32_t n2 = (int32_t)((double)(r1 - r0) * (fq < fs ? fq : fs));
+                        r1 = r0 + max(1, min(n2, r1 - r0 - 1));
                     }
                     const uint32_t db = (uint32_t)(r1 - r0) * (uint32_t)sizeof(ReadDesc);
                     const uint32_t qbytes = staged ? (uint32_t)(qb - qa) : 0u, sbytes = staged ? (uint32_t)(sb - sa) : 0u;
@@ -710,6 +776,9 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
                     sm.info[s] = ci;
                     mbar_arrive(&sm.full[s]);
                 }
+#ifdef BRC_K1_PROFILE
+                atomicAdd(&g_k1prof[2], (unsigned long long)(tp1 - tp0)); atomicAdd(&g_k1prof[3], (unsigned long long)(clock64() - tp1)); atomicAdd(&g_k1prof[4], 1ull);
+#endif
                 item++; first = false; r0 = r1;
             } while (r0 < hi);
             if (done) break;
@@ -719,19 +788,27 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
 
     // =========================== CONSUMERS ===========================
     SiteState S0;
-    S0.tid = tid; S0.warp0 = tid & ~31;
     for (uint32_t item = 0;; ++item) {
         const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
-        mbar_wait(&sm.full[s], ph);
-        const ChunkInfo ci = sm.info[s];
+#ifdef BRC_K1_PROFILE
+        const long long tc0 = clock64();
+#endif
+        mbar_wait_hint<2000>(&sm.full[s], ph);
+#ifdef BRC_K1_PROFILE
+        const long long tc1 = clock64();
+#endif
+        const ChunkInfo &ci = sm.info[s];   // stays valid until this warp arrives on empty[s]
         if (ci.work < 0) break;
-        if (ci.flags & 2u) site_reset(S0, ci);   // first chunk of a tile
+        if (ci.flags & 2u) site_reset(S0, ci, tid);   // first chunk of a tile
         if (!S0.warp_done) {
-            if (ci.flags & 1u) process_chunk<PER_LIB, true>(P, sm.st[s], sm.sacc, ci, S0);
-            else process_chunk<PER_LIB, false>(P, sm.st[s], sm.sacc, ci, S0);
+            if (ci.flags & 1u) process_chunk<PER_LIB, true>(P, sm.st[s], sm.sacc, ci, S0, tid);
+            else process_chunk<PER_LIB, false>(P, sm.st[s], sm.sacc, ci, S0, tid);
         }
-        if (ci.flags & 4u) site_emit(P, sm.sacc, ci, S0);   // last chunk of the tile
+        if (ci.flags & 4u) site_emit(P, sm.sacc, ci, S0, tid);   // last chunk of the tile
         __syncwarp();
+#ifdef BRC_K1_PROFILE
+        if (lane == 0) { atomicAdd(&g_k1prof[0], (unsigned long long)(tc1 - tc0)); atomicAdd(&g_k1prof[1], (unsigned long long)(clock64() - tc1)); }
+#endif
         if (lane == 0) mbar_arrive(&sm.empty[s]);   // this warp is done with the slot
     }
     // warning counters: warp-reduce then one atomic per warp
@@ -744,6 +821,13 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_kernel(PileupParams P) {
 }
 
 static int g_sm_count[64] = {0};
+#ifdef BRC_K1_PROFILE
+extern "C" __attribute__((visibility("default"))) void brc_debug_k1prof(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_k1prof, sizeof(g_k1prof));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_k1prof, z, sizeof(z)); }
+}
+#endif
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
     if (p.n_tiles == 0) return cudaSuccess;
     int dev = 0; cudaGetDevice(&dev);
@@ -756,7 +840,7 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
     }
     const int sms = dev < 64 && g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
     const int64_t n_work = p.n_tiles * (int64_t)p.res.n_rows;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_work, (int64_t)sms * 3);   // persistent: 3 CTAs per SM
+    const unsigned grid = (unsigned)std::min<int64_t>(n_work, (int64_t)sms * BRC_K1_CTAS_PER_SM);   // persistent CTAs
     const size_t smem = sizeof(PileupSmem);
     if (p.per_lib) pileup_kernel<true><<<grid, K1_THREADS, smem, s>>>(p);
     else pileup_kernel<false><<<grid, K1_THREADS, smem, s>>>(p);
