@@ -136,7 +136,9 @@ struct PileupParams {
     const TileInfo *tiles;
     const int32_t *tile_lo;
     const int32_t *tile_hi;
-    int64_t n_tiles;
+    int64_t n_tiles;       // tiles of the whole plan
+    int64_t tile_begin;    // this launch covers tiles [tile_begin, tile_begin + tile_count)
+    int64_t tile_count;
     ResultsDev res;
 };
 
@@ -149,6 +151,8 @@ struct PrecomputeParams {
     ReadDesc *desc;
     int32_t *tile_lo;
     int32_t *tile_hi;
+    int64_t read_begin;    // this launch covers reads [read_begin, read_end)
+    int64_t read_end;
 };
 
 // launch wrappers (brc_kernels.cu)

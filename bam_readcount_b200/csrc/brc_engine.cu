@@ -6,6 +6,7 @@
 // host, in file order), end_region ≙ bam_plbuf_push(0).  All arithmetic of the hot path runs
 // in the CUDA kernels of brc_kernels.cu; this file only batches, copies and launches.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -80,6 +81,9 @@ void brc_destroy(brc_engine *e) {
                       &e->h_sec_kind, &e->h_sec_len, &e->h_sec_read, &e->h_sec_qpos, &e->h_sec_stats, &e->h_misc};
     for (auto *b : pins) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->pipe_ev) if (ev) cudaEventDestroy(ev);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -374,18 +378,24 @@ static int upload_geometry(brc_engine *e, cudaStream_t s) {
     return BRC_OK;
 }
 
-// K(init) + K0 + K1 on stream s.  Returns BRC_E_OVERFLOW (after syncing) if the secondary pool was too small.
-static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStream_t s, bool check_overflow) {
-    PrecomputeParams P0{};
+static void make_params(brc_engine *e, const int32_t *d_region_of_read, PrecomputeParams &P0, PileupParams &P1) {
+    P0 = PrecomputeParams{};
     P0.reads = e->dev_reads; P0.regions = e->d_regions.as<RegionDev>(); P0.n_regions = (int64_t)e->regions_dev.size();
     P0.region_of_read = d_region_of_read; P0.refs = e->d_refs.as<RefWin>(); P0.desc = e->d_desc.as<ReadDesc>();
     P0.tile_lo = e->d_tile_lo.as<int32_t>(); P0.tile_hi = e->d_tile_hi.as<int32_t>();
-    PileupParams P1{};
+    P0.read_begin = 0; P0.read_end = e->dev_reads.n_reads;
+    P1 = PileupParams{};
     P1.min_mapq = e->cfg.min_mapq; P1.min_bq = e->cfg.min_bq; P1.per_lib = e->cfg.per_lib; P1.insertion_centric = e->cfg.insertion_centric;
     P1.desc = e->d_desc.as<ReadDesc>(); P1.cigar = e->dev_reads.cigar; P1.seq = e->dev_reads.seq; P1.qual = e->dev_reads.qual;
     P1.seq_off = e->dev_reads.seq_off; P1.qual_off = e->dev_reads.qual_off;
-    P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size();
+    P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size(); P1.tile_begin = 0; P1.tile_count = P1.n_tiles;
     P1.res = results_dev(e);
+}
+
+// K(init) + K0 + K1 on stream s.  Returns BRC_E_OVERFLOW (after syncing) if the secondary pool was too small.
+static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStream_t s, bool check_overflow) {
+    PrecomputeParams P0; PileupParams P1;
+    make_params(e, d_region_of_read, P0, P1);
 
     e->launch_count = 0;
     CU(cudaEventRecord(e->ev[0], s), "event");
@@ -404,7 +414,7 @@ static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStrea
     return BRC_OK;
 }
 
-static int fetch_results(brc_engine *e, cudaStream_t s) {
+static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetched = false) {
     const int64_t rs = (int64_t)e->n_rows * e->n_slots;
     int32_t cnt = 0;
     CU(cudaMemcpyAsync(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost, s), "D2H sec_count");
@@ -417,7 +427,7 @@ static int fetch_results(brc_engine *e, cudaStream_t s) {
     CU(e->h_sec_next.reserve(ns1 * 4), "pin"); CU(e->h_sec_kind.reserve(ns1), "pin"); CU(e->h_sec_len.reserve(ns1 * 4), "pin");
     CU(e->h_sec_read.reserve(ns1 * 8), "pin"); CU(e->h_sec_qpos.reserve(ns1 * 4), "pin"); CU(e->h_sec_stats.reserve(ns1 * 4 * N_STATS), "pin");
     CU(e->h_misc.reserve(64), "pin");
-    if (rs) {
+    if (rs && !slots_already_fetched) {
         CU(cudaMemcpyAsync(e->h_ncover.p, e->d_ncover.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
         CU(cudaMemcpyAsync(e->h_npass.p, e->d_npass.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
         CU(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, rs, cudaMemcpyDeviceToHost, s), "D2H");
@@ -455,6 +465,99 @@ static int fetch_results(brc_engine *e, cudaStream_t s) {
     return BRC_OK;
 }
 
+// Push path, one borrowed region: stream the batch through the GPU in read-index chunks so that the H2D copy of
+// chunk c+1, the kernels of chunk c and the D2H copy of the finished tiles of chunk c-1 overlap (PCIe is full
+// duplex; three streams + events).  Reads are position-sorted, so every tile that ends at or before the first
+// position of chunk c+1 is complete once chunk c is on the device.
+static int compute_pipelined(brc_engine *e) {
+    const brc_read_batch &B = e->borrowed;
+    const int64_t n = B.n_reads;
+    const brc_region &rg = e->regions[0];
+    const int64_t n_tiles = (int64_t)e->tiles.size();
+    const int64_t rs = (int64_t)e->n_rows * e->n_slots;
+    if (!e->s_in) CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking), "stream");
+    if (!e->s_out) CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking), "stream");
+    const uint64_t n_cig = B.cigar_off[n], n_seq = B.seq_off[n], n_qual = B.qual_off[n];
+    const size_t tot[13] = {(size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 2, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
+                            (size_t)(n + 1) * 8, (size_t)n_cig * 4, (size_t)(n + 1) * 8, (size_t)n_seq, (size_t)(n + 1) * 8, (size_t)n_qual};
+    for (int k = 0; k < 13; ++k) CU(e->d_in[k].reserve(tot[k] + 16), "cudaMalloc(reads)");
+    ReadsDev &R = e->dev_reads;
+    R.n_reads = n; R.pos = e->d_in[0].as<int32_t>(); R.flag = e->d_in[1].as<uint16_t>(); R.mapq = e->d_in[2].as<uint8_t>();
+    R.lib = e->d_in[3].as<uint16_t>(); R.l_qseq = e->d_in[4].as<int32_t>(); R.nm = e->d_in[5].as<int32_t>(); R.sm = e->d_in[6].as<int32_t>();
+    R.cigar_off = e->d_in[7].as<uint64_t>(); R.cigar = e->d_in[8].as<uint32_t>(); R.seq_off = e->d_in[9].as<uint64_t>();
+    R.seq = e->d_in[10].as<uint8_t>(); R.qual_off = e->d_in[11].as<uint64_t>(); R.qual = e->d_in[12].as<uint8_t>();
+    // host result buffers
+    const int64_t rs1 = std::max<int64_t>(rs, 1);
+    CU(e->h_ncover.reserve(rs1 * 4), "pin"); CU(e->h_npass.reserve(rs1 * 4), "pin"); CU(e->h_flags.reserve(rs1), "pin");
+    CU(e->h_pbase.reserve(rs1), "pin"); CU(e->h_sec_head.reserve(rs1 * 4), "pin"); CU(e->h_pstats.reserve(rs1 * 4 * N_STATS), "pin");
+
+    const size_t in_bytes = tot[0] + tot[1] + tot[2] + tot[3] + tot[4] + tot[5] + tot[6] + tot[7] + tot[8] + tot[9] + tot[10] + tot[11] + tot[12];
+    int n_chunks = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(in_bytes >> 26)));   // ~64 MiB of input per chunk
+    n_chunks = (int)std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 4096));
+    if (const char *ov = std::getenv("BRC_PIPE_CHUNKS")) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::atoi(ov), std::max<int64_t>(1, n)));   // test hook
+    while (e->pipe_ev.size() < (size_t)(2 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
+
+    PrecomputeParams P0; PileupParams P1;
+    make_params(e, nullptr, P0, P1);
+    cudaStream_t sk = e->stream;
+    e->launch_count = 0;
+    CU(cudaEventRecord(e->ev[0], sk), "event");
+    CU(launch_init_tiles(P0.tile_lo, P0.tile_hi, n_tiles, P1.res.sec_count, P1.res.warn, sk), "launch init_tiles"); e->launch_count++;
+    if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, e->s_in), "memset lib");
+    int64_t tile_done = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
+        // ---- H2D of reads [a, b) (offsets [a, b]) ----
+        #define H2D(k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, e->s_in), "H2D chunk")
+        H2D(0, B.pos, a, b - a, 4); H2D(1, B.flag, a, b - a, 2); H2D(2, B.mapq, a, b - a, 1);
+        if (B.lib) H2D(3, B.lib, a, b - a, 2);
+        H2D(4, B.l_qseq, a, b - a, 4); H2D(5, B.nm, a, b - a, 4); H2D(6, B.sm, a, b - a, 4);
+        H2D(7, B.cigar_off, a, b - a + 1, 8); H2D(8, B.cigar, B.cigar_off[a], B.cigar_off[b] - B.cigar_off[a], 4);
+        H2D(9, B.seq_off, a, b - a + 1, 8); H2D(10, B.seq, B.seq_off[a], B.seq_off[b] - B.seq_off[a], 1);
+        H2D(11, B.qual_off, a, b - a + 1, 8); H2D(12, B.qual, B.qual_off[a], B.qual_off[b] - B.qual_off[a], 1);
+        #undef H2D
+        CU(cudaEventRecord(e->pipe_ev[2 * c], e->s_in), "event");
+        // ---- kernels: K0 on the chunk, K1 on the tiles it completes ----
+        CU(cudaStreamWaitEvent(sk, e->pipe_ev[2 * c], 0), "wait");
+        P0.read_begin = a; P0.read_end = b;
+        CU(launch_precompute(P0, sk), "launch read_precompute"); e->launch_count++;
+        int64_t tile_to = n_tiles;
+        if (c + 1 < n_chunks) {
+            const int64_t next_pos = B.pos[b];
+            tile_to = next_pos <= rg.first_pos ? 0 : std::min<int64_t>(n_tiles, (next_pos - rg.first_pos) / TILE);
+            tile_to = std::max(tile_to, tile_done);
+        }
+        if (tile_to > tile_done) {
+            P1.tile_begin = tile_done; P1.tile_count = tile_to - tile_done;
+            CU(launch_pileup(P1, sk), "launch pileup"); e->launch_count++;
+            CU(cudaEventRecord(e->pipe_ev[2 * c + 1], sk), "event");
+            // ---- D2H of the finished slots ----
+            CU(cudaStreamWaitEvent(e->s_out, e->pipe_ev[2 * c + 1], 0), "wait");
+            const int64_t s0 = e->tiles[(size_t)tile_done].slot0;
+            const int64_t s1 = tile_to < n_tiles ? e->tiles[(size_t)tile_to].slot0 : e->n_slots;
+            const size_t w = (size_t)(s1 - s0);
+            const size_t pitch4 = (size_t)e->n_slots * 4, pitch1 = (size_t)e->n_slots;
+            const int rows = e->n_rows;
+            CU(cudaMemcpy2DAsync((char *)e->h_ncover.p + s0 * 4, pitch4, (char *)e->d_ncover.p + s0 * 4, pitch4, w * 4, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            CU(cudaMemcpy2DAsync((char *)e->h_npass.p + s0 * 4, pitch4, (char *)e->d_npass.p + s0 * 4, pitch4, w * 4, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            CU(cudaMemcpy2DAsync((char *)e->h_flags.p + s0, pitch1, (char *)e->d_flags.p + s0, pitch1, w, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            CU(cudaMemcpy2DAsync((char *)e->h_pbase.p + s0, pitch1, (char *)e->d_pbase.p + s0, pitch1, w, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            CU(cudaMemcpy2DAsync((char *)e->h_sec_head.p + s0 * 4, pitch4, (char *)e->d_sec_head.p + s0 * 4, pitch4, w * 4, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            CU(cudaMemcpy2DAsync((char *)e->h_pstats.p + s0 * 4, pitch4, (char *)e->d_pstats.p + s0 * 4, pitch4, w * 4, (size_t)rows * N_STATS, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            tile_done = tile_to;
+        }
+    }
+    CU(cudaEventRecord(e->ev[1], sk), "event");
+    CU(cudaEventRecord(e->ev[2], sk), "event");
+    CU(cudaStreamSynchronize(sk), "sync kernels");
+    CU(cudaStreamSynchronize(e->s_out), "sync D2H");
+    int32_t cnt = 0;
+    CU(cudaMemcpy(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost), "D2H sec_count");
+    e->h_n_sec = cnt;
+    if ((int64_t)cnt > e->sec_cap) return BRC_E_OVERFLOW;
+    return fetch_results(e, sk, true);
+}
+
 extern "C" {
 
 int brc_compute(brc_engine *e) {
@@ -482,6 +585,16 @@ int brc_compute(brc_engine *e) {
     rc = alloc_outputs(e, n);
     if (rc != BRC_OK) return rc;
     cudaStream_t s = e->stream;
+    if (bw && e->regions.size() == 1 && n > 0 && !e->tiles.empty()) {
+        rc = upload_geometry(e, s);
+        if (rc != BRC_OK) return rc;
+        int64_t cap0 = std::max<int64_t>(e->sec_cap, (int64_t)e->n_rows * e->n_slots / 8 + 2 * e->n_indel_ops + 1024);
+        rc = alloc_sec(e, cap0);
+        if (rc != BRC_OK) return rc;
+        rc = compute_pipelined(e);
+        if (rc != BRC_E_OVERFLOW) return rc;
+        // pool too small: everything is on the device already; fall through to the plain path with a larger pool
+    }
     // H2D of the read arrays (borrowed batches: straight from the caller's buffers)
     std::vector<uint16_t> zero_lib;
     const uint16_t *h_lib = bw ? B.lib : H.lib.data();

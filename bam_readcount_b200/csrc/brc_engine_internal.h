@@ -75,6 +75,8 @@ struct brc_engine {
     brc_config cfg{};
     int n_rows = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined push path
+    std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 

@@ -186,8 +186,8 @@ struct __align__(128) K0Smem {
 __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputeParams P) {
     __shared__ K0Smem ks;
     const ReadsDev &R = P.reads;
-    const int64_t r0 = blockIdx.x * (int64_t)K0_READS;
-    const int64_t r1 = min(r0 + (int64_t)K0_READS, R.n_reads);
+    const int64_t r0 = P.read_begin + blockIdx.x * (int64_t)K0_READS;
+    const int64_t r1 = min(r0 + (int64_t)K0_READS, P.read_end);
     const int64_t i = r0 + threadIdx.x;
 
     // stage the block's byte ranges (uniform decision)
@@ -366,8 +366,9 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
 cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s) {
     cudaError_t e = ensure_tables();
     if (e != cudaSuccess) return e;
-    if (p.reads.n_reads == 0) return cudaSuccess;
-    read_precompute_kernel<<<(unsigned)((p.reads.n_reads + K0_READS - 1) / K0_READS), K0_READS, 0, s>>>(p);
+    const int64_t n = p.read_end - p.read_begin;
+    if (n <= 0) return cudaSuccess;
+    read_precompute_kernel<<<(unsigned)((n + K0_READS - 1) / K0_READS), K0_READS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
     PileupSmem &sm = *reinterpret_cast<PileupSmem *>(smem_raw);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int64_t n_work = P.n_tiles * (int64_t)P.res.n_rows;
+    const int64_t n_work = P.tile_count * (int64_t)P.res.n_rows;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], N_CONSUMER_WARPS); }
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
             const bool done = w >= n_work;
             int32_t lo = 0, hi = 0; TileInfo ti{0, 0, 0}; uint32_t row = 0;
             if (!done) {
-                const int64_t tile = w % P.n_tiles; row = (uint32_t)(w / P.n_tiles);
+                const int64_t tile = P.tile_begin + w % P.tile_count; row = (uint32_t)(w / P.tile_count);
                 ti = P.tiles[tile]; lo = P.tile_lo[tile]; hi = P.tile_hi[tile];
                 if (lo >= hi) { lo = 0; hi = 0; }
             }
@@ -829,7 +830,7 @@ extern "C" __attribute__((visibility("default"))) void brc_debug_k1prof(unsigned
 }
 #endif
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
-    if (p.n_tiles == 0) return cudaSuccess;
+    if (p.tile_count <= 0) return cudaSuccess;
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 64 && g_sm_count[dev] == 0) {
         cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
@@ -839,7 +840,7 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
         if (e2 != cudaSuccess) return e2;
     }
     const int sms = dev < 64 && g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
-    const int64_t n_work = p.n_tiles * (int64_t)p.res.n_rows;
+    const int64_t n_work = p.tile_count * (int64_t)p.res.n_rows;
     const unsigned grid = (unsigned)std::min<int64_t>(n_work, (int64_t)sms * BRC_K1_CTAS_PER_SM);   // persistent CTAs
     const size_t smem = sizeof(PileupSmem);
     if (p.per_lib) pileup_kernel<true><<<grid, K1_THREADS, smem, s>>>(p);

@@ -103,3 +103,15 @@ def test_borrowed_and_copied_batches_agree():
         finally:
             eng.close()
     assert outs[0] == outs[1] and len(outs[0]) > 100000
+
+
+def test_pipelined_push_path_many_chunks(monkeypatch):
+    """The borrowed push path streams the batch in read-index chunks (H2D / kernels / D2H overlapped); force many
+    tiny chunks and check every accumulator against the oracle."""
+    monkeypatch.setenv("BRC_PIPE_CHUNKS", "7")
+    case = cases.synthetic_case(L=20000, depth=30, seed=13, regions=((0, 1, 20000),), site_list=False)
+    for flags in (dict(), dict(per_lib=True, insertion_centric=True, min_mapq=20, min_bq=20)):
+        otext, odump, _ = cases.run_oracle(case, flags, site_list=True)
+        etext, edump, _, _ = cases.run_engine(case, flags, site_list=True)
+        assert etext == otext
+        assert edump == odump
