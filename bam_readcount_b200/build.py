@@ -55,5 +55,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI = os.path.join(HERE, "brc-readcount")
+
+
+def build_cli(force: bool = False) -> str:
+    """The C++ host binary (same CLI / STDOUT as bam-readcount) on top of libbrc_engine.so."""
+    src = os.path.join(CSRC, "brc_cli.cpp")
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return CLI
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI, src, "-I", os.path.join(HERE, "..", "include"),
+           "-L", HERE, "-lbrc_engine", "-lz", "-Wl,-rpath,$ORIGIN"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout)
+        raise RuntimeError("g++ failed building brc-readcount")
+    return CLI
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_cli(force="--force" in sys.argv))

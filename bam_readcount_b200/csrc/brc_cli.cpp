@@ -1,0 +1,439 @@
+// brc_cli.cpp — `brc-readcount`: the C++ host.  Same command line and STDOUT as bam-readcount
+// (R:src/exe/bam-readcount/bamreadcount.cpp:421-670), with the pileup hot path routed through
+// libbrc_engine.so (include/brc_engine.h).  File decode stays on the host, as the north star says:
+// a small BGZF/BAM/BAI/FASTA reader written against the SAM specification (zlib for inflate);
+// htslib is not linked.  CRAM input is not supported by this host.
+//
+// Mirrors, region by region, the reference's two loops:
+//   -l site list : R:...:574-608  (d.beg=beg-1, d.end=end, queues cleared per region)
+//   argv regions : R:...:641-657  (bam_parse_region; a bare contig name keeps the previous beg/end, A.6)
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <getopt.h>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+#include "../../include/brc_engine.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// BGZF (SAM spec §4.1): random access by virtual offset (coffset<<16 | uoffset)
+// ------------------------------------------------------------------------------------------
+struct Bgzf {
+    FILE *fp = nullptr;
+    std::vector<uint8_t> block, raw;
+    uint64_t block_coff = 0;     // compressed offset of the current block
+    uint64_t next_coff = 0;      // compressed offset of the next block
+    size_t upos = 0;             // position inside `block`
+    bool eof = false;
+
+    bool open(const std::string &path) { fp = std::fopen(path.c_str(), "rb"); return fp != nullptr; }
+    ~Bgzf() { if (fp) std::fclose(fp); }
+
+    bool load_block(uint64_t coff) {
+        if (fseeko(fp, (off_t)coff, SEEK_SET) != 0) return false;
+        uint8_t h[18];
+        if (std::fread(h, 1, 18, fp) != 18) { eof = true; block.clear(); upos = 0; return false; }
+        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return false;
+        const uint16_t xlen = (uint16_t)(h[10] | (h[11] << 8));
+        // BC subfield is first in every BGZF writer; scan anyway
+        std::vector<uint8_t> extra(xlen);
+        std::memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
+        if (xlen > 6 && std::fread(extra.data() + 6, 1, xlen - 6, fp) != (size_t)(xlen - 6)) return false;
+        int bsize = -1;
+        for (size_t i = 0; i + 4 <= xlen;) {
+            const uint16_t sl = (uint16_t)(extra[i + 2] | (extra[i + 3] << 8));
+            if (extra[i] == 'B' && extra[i + 1] == 'C' && sl == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+            i += 4 + sl;
+        }
+        if (bsize < 0) return false;
+        const size_t clen = (size_t)bsize + 1 - 12 - xlen - 8;
+        raw.resize(clen + 8);
+        if (std::fread(raw.data(), 1, clen + 8, fp) != clen + 8) return false;
+        const uint32_t isize = raw[clen + 4] | (raw[clen + 5] << 8) | (raw[clen + 6] << 16) | ((uint32_t)raw[clen + 7] << 24);
+        block.resize(isize);
+        if (isize) {
+            z_stream zs{};
+            if (inflateInit2(&zs, -15) != Z_OK) return false;
+            zs.next_in = raw.data(); zs.avail_in = (uInt)clen; zs.next_out = block.data(); zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END) return false;
+        }
+        block_coff = coff; next_coff = coff + (uint64_t)bsize + 1; upos = 0; eof = false;
+        return true;
+    }
+    bool seek(uint64_t voff) {
+        if (!load_block(voff >> 16)) return false;
+        upos = (size_t)(voff & 0xFFFF);
+        return true;
+    }
+    uint64_t tell() const { return (block_coff << 16) | (uint64_t)upos; }
+    // read exactly n bytes (spanning blocks); false at EOF
+    bool read(void *dst, size_t n) {
+        uint8_t *d = (uint8_t *)dst;
+        while (n) {
+            if (upos >= block.size()) {
+                if (!load_block(next_coff)) return false;
+                if (block.empty()) { if (eof) return false; continue; }
+            }
+            const size_t k = std::min(n, block.size() - upos);
+            std::memcpy(d, block.data() + upos, k);
+            d += k; upos += k; n -= k;
+        }
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// BAM header + BAI index (SAM spec §4.2, §5.2)
+// ------------------------------------------------------------------------------------------
+struct BamFile {
+    Bgzf bz;
+    std::string text;
+    std::vector<std::string> names;
+    std::vector<int32_t> lens;
+    std::map<std::string, int> tid_of;
+    uint64_t first_rec = 0;
+    // BAI
+    struct RefIdx { std::vector<uint64_t> linear; uint64_t min_chunk = ~0ull; };
+    std::vector<RefIdx> idx;
+    bool have_idx = false;
+
+    bool open(const std::string &path) {
+        if (!bz.open(path) || !bz.load_block(0)) return false;
+        char magic[4]; int32_t l_text, n_ref;
+        if (!bz.read(magic, 4) || std::memcmp(magic, "BAM\1", 4) != 0) return false;
+        if (!bz.read(&l_text, 4)) return false;
+        text.resize((size_t)l_text);
+        if (l_text && !bz.read(&text[0], (size_t)l_text)) return false;
+        text = text.c_str();
+        if (!bz.read(&n_ref, 4)) return false;
+        for (int i = 0; i < n_ref; ++i) {
+            int32_t ln, sl;
+            if (!bz.read(&ln, 4)) return false;
+            std::string nm((size_t)ln, 0);
+            if (!bz.read(&nm[0], (size_t)ln) || !bz.read(&sl, 4)) return false;
+            nm = nm.c_str();
+            tid_of[nm] = i; names.push_back(nm); lens.push_back(sl);
+        }
+        first_rec = bz.tell();
+        return true;
+    }
+    bool load_index(const std::string &bam_path) {
+        std::string p = bam_path + ".bai";
+        FILE *f = std::fopen(p.c_str(), "rb");
+        if (!f && bam_path.size() > 4) { p = bam_path.substr(0, bam_path.size() - 4) + ".bai"; f = std::fopen(p.c_str(), "rb"); }
+        if (!f) return false;
+        auto rd = [&](void *d, size_t n) { return std::fread(d, 1, n, f) == n; };
+        char magic[4]; int32_t n_ref;
+        bool ok = rd(magic, 4) && std::memcmp(magic, "BAI\1", 4) == 0 && rd(&n_ref, 4);
+        idx.assign((size_t)std::max(n_ref, 0), RefIdx());
+        for (int r = 0; ok && r < n_ref; ++r) {
+            int32_t n_bin; ok = rd(&n_bin, 4);
+            for (int b = 0; ok && b < n_bin; ++b) {
+                uint32_t bin; int32_t n_chunk; ok = rd(&bin, 4) && rd(&n_chunk, 4);
+                for (int c = 0; ok && c < n_chunk; ++c) {
+                    uint64_t cb, ce; ok = rd(&cb, 8) && rd(&ce, 8);
+                    if (ok && bin != 37450) idx[(size_t)r].min_chunk = std::min(idx[(size_t)r].min_chunk, cb);
+                }
+            }
+            int32_t n_intv; ok = ok && rd(&n_intv, 4);
+            if (ok) { idx[(size_t)r].linear.resize((size_t)n_intv); ok = n_intv == 0 || rd(idx[(size_t)r].linear.data(), 8 * (size_t)n_intv); }
+        }
+        std::fclose(f);
+        have_idx = ok;
+        return ok;
+    }
+    // smallest virtual offset of a record that can overlap position `beg` on `tid` (linear index, 16 kb windows)
+    bool query_offset(int tid, int64_t beg, uint64_t &voff) const {
+        if (tid < 0 || tid >= (int)idx.size()) return false;
+        const RefIdx &ri = idx[(size_t)tid];
+        if (ri.min_chunk == ~0ull) return false;                      // no alignments on this reference
+        int64_t w = beg >> 14;
+        voff = ri.min_chunk;
+        if (!ri.linear.empty()) {
+            if (w >= (int64_t)ri.linear.size()) w = (int64_t)ri.linear.size() - 1;
+            for (; w >= 0; --w) if (ri.linear[(size_t)w] != 0) { voff = std::max(voff, ri.linear[(size_t)w]); break; }
+        }
+        return true;
+    }
+};
+
+struct Rec {   // one decoded alignment (the bam1_t fields the path reads)
+    int32_t tid, pos, l_qseq, nm, sm; uint16_t flag; uint8_t mapq; uint32_t n_cigar;
+    std::vector<uint8_t> data;   // whole record body
+    const uint32_t *cigar; const uint8_t *seq, *qual; std::string rg; bool has_rg;
+};
+
+int64_t aux_int(const uint8_t *p, char t) {
+    switch (t) {
+    case 'c': return (int8_t)p[0]; case 'C': return p[0];
+    case 's': { int16_t v; std::memcpy(&v, p, 2); return v; } case 'S': { uint16_t v; std::memcpy(&v, p, 2); return v; }
+    case 'i': { int32_t v; std::memcpy(&v, p, 4); return v; } case 'I': { uint32_t v; std::memcpy(&v, p, 4); return v; }
+    default: return 0;
+    }
+}
+
+bool read_record(Bgzf &bz, Rec &r) {
+    int32_t bs;
+    if (!bz.read(&bs, 4) || bs < 32) return false;
+    r.data.resize((size_t)bs);
+    if (!bz.read(r.data.data(), (size_t)bs)) return false;
+    const uint8_t *d = r.data.data();
+    int32_t refid, pos, l_seq; uint8_t l_rn, mapq; uint16_t n_cig, flag;
+    std::memcpy(&refid, d, 4); std::memcpy(&pos, d + 4, 4); l_rn = d[8]; mapq = d[9];
+    std::memcpy(&n_cig, d + 12, 2); std::memcpy(&flag, d + 14, 2); std::memcpy(&l_seq, d + 16, 4);
+    r.tid = refid; r.pos = pos; r.mapq = mapq; r.flag = flag; r.n_cigar = n_cig; r.l_qseq = l_seq;
+    size_t o = 32 + l_rn;
+    r.cigar = (const uint32_t *)(d + o); o += 4 * (size_t)n_cig;
+    r.seq = d + o; o += ((size_t)l_seq + 1) / 2;
+    r.qual = d + o; o += (size_t)l_seq;
+    r.nm = BRC_TAG_ABSENT; r.sm = BRC_TAG_ABSENT; r.has_rg = false;
+    bool got_nm = false, got_sm = false;
+    while (o + 3 <= (size_t)bs) {          // bam_aux_get's linear scan: first occurrence wins
+        const uint8_t *t = d + o; const char ty = (char)t[2]; o += 3;
+        size_t sz = 0;
+        switch (ty) {
+        case 'A': case 'c': case 'C': sz = 1; break;
+        case 's': case 'S': sz = 2; break;
+        case 'i': case 'I': case 'f': sz = 4; break;
+        case 'Z': case 'H': { size_t e = o; while (e < (size_t)bs && d[e]) ++e; if (ty == 'Z' && t[0] == 'R' && t[1] == 'G' && !r.has_rg) { r.rg.assign((const char *)d + o, e - o); r.has_rg = true; } o = e + 1; continue; }
+        case 'B': { const char st = (char)d[o]; uint32_t cnt; std::memcpy(&cnt, d + o + 1, 4); size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; o += 5 + es * cnt; continue; }
+        default: o = (size_t)bs; continue;
+        }
+        if (t[0] == 'N' && t[1] == 'M' && !got_nm && ty != 'A' && ty != 'f') { r.nm = (int32_t)aux_int(d + o, ty); got_nm = true; }
+        if (t[0] == 'S' && t[1] == 'M' && !got_sm && ty != 'A' && ty != 'f') { r.sm = (int32_t)aux_int(d + o, ty); got_sm = true; }
+        o += sz;
+    }
+    return true;
+}
+
+int64_t rec_endpos(const Rec &r) {   // bam_endpos
+    if (!(r.flag & 4) && r.n_cigar > 0) {
+        int64_t l = 0;
+        for (uint32_t k = 0; k < r.n_cigar; ++k) { uint32_t op = r.cigar[k] & 0xF; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) l += r.cigar[k] >> 4; }
+        return r.pos + l;
+    }
+    return (int64_t)r.pos + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// FASTA + .fai (fai_fetch of a whole chromosome, R:...:87)
+// ------------------------------------------------------------------------------------------
+struct Fasta {
+    std::string path;
+    struct Ent { int64_t len, off, lb, lw; };
+    std::map<std::string, Ent> ents;
+    bool open(const std::string &p) {
+        path = p;
+        std::ifstream f(p + ".fai");
+        if (!f) return false;
+        std::string line;
+        while (std::getline(f, line)) { std::istringstream ss(line); std::string n; Ent e; if (ss >> n >> e.len >> e.off >> e.lb >> e.lw) ents[n] = e; }
+        return true;
+    }
+    bool fetch(const std::string &name, std::string &out) const {
+        auto it = ents.find(name);
+        if (it == ents.end()) return false;
+        const Ent &e = it->second;
+        FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) return false;
+        const int64_t n_lines = (e.len + e.lb - 1) / e.lb;
+        std::vector<char> raw((size_t)(n_lines * e.lw + 8));
+        fseeko(f, (off_t)e.off, SEEK_SET);
+        const size_t got = std::fread(raw.data(), 1, raw.size(), f);
+        std::fclose(f);
+        out.clear(); out.reserve((size_t)e.len);
+        for (size_t i = 0; i < got && (int64_t)out.size() < e.len; ++i) if (raw[i] != '\n' && raw[i] != '\r') out.push_back(raw[i]);
+        return (int64_t)out.size() == e.len;
+    }
+};
+
+void usage() {
+    std::printf("Usage: bam-readcount [OPTIONS] bam_file|cram_file [region]\nGenerate metrics for bam_file at single nucleotide positions.\n"
+                "Example: bam-readcount -f ref.fa some.bam|some.cram\n\nAvailable options:\n"
+                "  -h [ --help ]                         produce this message\n"
+                "  -v [ --version ]                      output the version number\n"
+                "  -q [ --min-mapping-quality ] arg (=0) minimum mapping quality of reads used for counting.\n"
+                "  -b [ --min-base-quality ] arg (=0)    minimum base quality at a position to use the read for counting.\n"
+                "  -d [ --max-count ] arg (=10000000)    max depth to avoid excessive memory usage.\n"
+                "  -l [ --site-list ] arg                file containing a list of regions to report readcounts within.\n"
+                "  -f [ --reference-fasta ] arg          reference sequence in the fasta format.\n"
+                "  -D [ --print-individual-mapq ] arg    report the mapping qualities as a comma separated list.\n"
+                "  -p [ --per-library ]                  report results by library.\n"
+                "  -w [ --max-warnings ] arg             maximum number of warnings of each type to emit. -1 gives an unlimited number.\n"
+                "  -i [ --insertion-centric ]            generate indel centric readcounts. Reads containing insertions will not be\n"
+                "                                        included in per-base counts\n\n");
+}
+
+// samtools region string "name[:beg[-end]]"; returns 0 ok, -1 when only a name was given (beg/end untouched, A.6)
+int parse_region(const BamFile &bam, const std::string &s, int &tid, int &beg, int &end) {
+    std::string name = s; tid = -1;
+    size_t colon = s.rfind(':');
+    bool ranged = false;
+    int64_t b = 0, e = 0x7fffffff;
+    if (colon != std::string::npos && bam.tid_of.find(s) == bam.tid_of.end()) {
+        std::string coords = s.substr(colon + 1); name = s.substr(0, colon);
+        coords.erase(std::remove(coords.begin(), coords.end(), ','), coords.end());
+        char *endp = nullptr;
+        b = std::strtoll(coords.c_str(), &endp, 10);
+        if (endp && *endp == '-') e = std::strtoll(endp + 1, nullptr, 10);
+        else if (endp && *endp == 0) e = 0x7fffffff;
+        b = b > 0 ? b - 1 : 0;
+        ranged = true;
+    }
+    auto it = bam.tid_of.find(name);
+    if (it == bam.tid_of.end()) return -1;
+    tid = it->second;
+    if (!ranged) return -1;          // hts_parse_reg yields end = INT64_MAX -> bam_parse_region returns -1 after setting ref
+    beg = (int)b; end = (int)std::min<int64_t>(e, 0x7fffffff);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    int min_mapq = 0, min_bq = 0, max_cnt = 10000000; bool per_lib = false, ic = false; long long max_warn = -1;
+    std::string fn_pos, fn_fa, dist_arg;
+    static option lo[] = {{"help", 0, 0, 'h'}, {"version", 0, 0, 'v'}, {"min-mapping-quality", 1, 0, 'q'}, {"min-base-quality", 1, 0, 'b'},
+                          {"max-count", 1, 0, 'd'}, {"site-list", 1, 0, 'l'}, {"reference-fasta", 1, 0, 'f'}, {"print-individual-mapq", 1, 0, 'D'},
+                          {"per-library", 0, 0, 'p'}, {"max-warnings", 1, 0, 'w'}, {"insertion-centric", 0, 0, 'i'}, {0, 0, 0, 0}};
+    bool help = false, version = false;
+    for (int c; (c = getopt_long(argc, argv, "hvq:b:d:l:f:D:pw:i", lo, nullptr)) != -1;) {
+        switch (c) {
+        case 'h': help = true; break; case 'v': version = true; break;
+        case 'q': min_mapq = std::atoi(optarg); break; case 'b': min_bq = std::atoi(optarg); break; case 'd': max_cnt = std::atoi(optarg); break;
+        case 'l': fn_pos = optarg; break; case 'f': fn_fa = optarg; break; case 'D': dist_arg = optarg; break;
+        case 'p': per_lib = true; break; case 'w': max_warn = std::atoll(optarg); break; case 'i': ic = true; break;
+        default: usage(); return 1;
+        }
+    }
+    if (version) { std::printf("bam-readcount version: b200 (engine ABI %d)\n", brc_abi_version()); return 1; }   // R:...:467-470 (exit 1)
+    if (help || optind >= argc) { usage(); return 1; }                                                              // R:...:472-475
+    const std::string bam_path = argv[optind];
+    std::vector<std::string> region_args(argv + optind + 1, argv + argc);
+    std::fprintf(stderr, "Minimum mapping quality is set to %d\n", min_mapq);
+    if (dist_arg == "1" || dist_arg == "true") { std::fprintf(stderr, "Not currently supporting distributions\n"); return 1; }
+    (void)max_warn;
+
+    BamFile bam;
+    if (bam_path.size() > 5 && bam_path.substr(bam_path.size() - 5) == ".cram") { std::fprintf(stderr, "CRAM input is not supported by this host; convert to BAM\n"); return 1; }
+    if (!bam.open(bam_path)) { std::fprintf(stderr, "Fail to open BAM file %s\n", bam_path.c_str()); return 1; }
+    Fasta fa;
+    const bool have_fa = !fn_fa.empty() && fa.open(fn_fa);
+    if (!fn_fa.empty() && !have_fa) { std::fprintf(stderr, "Fail to open reference file %s\n", fn_fa.c_str()); return 1; }
+
+    // @RG ID -> LB; libraries in std::set order (R:...:92-111, 526-529)
+    std::map<std::string, std::string> rg_lb; std::set<std::string> libs;
+    {
+        std::istringstream ss(bam.text); std::string line;
+        while (std::getline(ss, line)) {
+            if (line.compare(0, 3, "@RG") != 0) continue;
+            std::istringstream ls(line); std::string tok, id, lb; bool has_lb = false;
+            while (std::getline(ls, tok, '\t')) { if (tok.compare(0, 3, "ID:") == 0) id = tok.substr(3); else if (tok.compare(0, 3, "LB:") == 0) { lb = tok.substr(3); has_lb = true; } }
+            if (has_lb) { libs.insert(lb); if (!id.empty() && !rg_lb.count(id)) rg_lb[id] = lb; }
+        }
+    }
+    for (const auto &l : libs) std::fprintf(stderr, "Expect library: %s in BAM\n", l.c_str());
+    std::vector<std::string> lib_names(libs.begin(), libs.end());
+    std::map<std::string, uint16_t> lib_rank;
+    for (size_t i = 0; i < lib_names.size(); ++i) lib_rank[lib_names[i]] = (uint16_t)i;
+    std::vector<const char *> lib_ptrs; for (auto &s : lib_names) lib_ptrs.push_back(s.c_str());
+    if (lib_ptrs.empty()) lib_ptrs.push_back("");
+
+    if (fn_pos.empty() && region_args.empty()) {
+        std::fprintf(stderr, "Whole-file mode is not supported (the reference skips its per-read pre-processing there, R:...:624); give regions or -l\n");
+        return 1;
+    }
+    if (!bam.load_index(bam_path)) { std::fprintf(stderr, "BAM indexing file is not available.\n"); return 1; }
+    if (!have_fa) { std::fprintf(stderr, "A reference FASTA (-f) is required in region / site-list mode\n"); return 1; }
+
+    brc_config cfg{}; cfg.min_mapq = min_mapq; cfg.min_bq = min_bq; cfg.max_cnt = max_cnt; cfg.per_lib = per_lib; cfg.insertion_centric = ic;
+    cfg.n_libs = (int32_t)lib_names.size(); cfg.device = std::getenv("BRC_DEVICE") ? std::atoi(std::getenv("BRC_DEVICE")) : 0;
+    brc_engine *eng = nullptr;
+    int rc = brc_create(&cfg, &eng);
+    if (rc != BRC_OK) { std::fprintf(stderr, "brc_create: %s\n", brc_strerror(rc)); return 1; }
+
+    struct Region { int tid, beg, end; bool site_list; };
+    std::vector<Region> regions;
+    if (!fn_pos.empty()) {
+        std::ifstream fp(fn_pos);
+        if (!fp) { std::fprintf(stderr, "Failed to open region list file: %s\n", fn_pos.c_str()); return 1; }
+        std::string line;
+        while (std::getline(fp, line)) {
+            std::istringstream ss(line); std::string name; int b, e;
+            if (!(ss >> name >> b >> e)) continue;
+            auto it = bam.tid_of.find(name);
+            if (it == bam.tid_of.end()) { std::fprintf(stderr, "%s not found in bam file. Region %s %i %i skipped.\n", name.c_str(), name.c_str(), b, e); continue; }
+            regions.push_back({it->second, b - 1, e, true});
+        }
+    } else {
+        int beg = 0, end = 0x7fffffff;
+        for (const auto &rs : region_args) {
+            int tid;
+            parse_region(bam, rs, tid, beg, end);
+            if (tid < 0) { std::fprintf(stderr, "Invalid region %s\n", rs.c_str()); brc_destroy(eng); return 1; }
+            regions.push_back({tid, beg, end, false});
+        }
+    }
+
+    std::set<int> ref_loaded;
+    std::string chrom;
+    Rec rec;
+    auto flush = [&]() -> int {
+        int r = brc_compute(eng);
+        if (r != BRC_OK) { std::fprintf(stderr, "brc_compute: %s\n", brc_last_error(eng)); return r; }
+        const int64_t need = brc_format_text(eng, -1, lib_ptrs.data(), nullptr, 0);
+        if (need < 0) { std::fprintf(stderr, "brc_format_text: %s\n", brc_last_error(eng)); return (int)need; }
+        std::vector<char> out((size_t)need + 1);
+        brc_format_text(eng, -1, lib_ptrs.data(), out.data(), need + 1);
+        std::fwrite(out.data(), 1, (size_t)need, stdout);
+        return brc_reset(eng);
+    };
+    int64_t pushed = 0;
+    for (size_t gi = 0; gi < regions.size(); ++gi) {
+        const Region &g = regions[gi];
+        if (!ref_loaded.count(g.tid)) {   // load_reference: whole chromosome
+            if (!fa.fetch(bam.names[(size_t)g.tid], chrom)) { std::fprintf(stderr, "Failed to fetch %s from %s\n", bam.names[(size_t)g.tid].c_str(), fn_fa.c_str()); brc_destroy(eng); return 1; }
+            rc = brc_set_reference(eng, g.tid, bam.names[(size_t)g.tid].c_str(), (int64_t)chrom.size(), 0, chrom.data(), (int64_t)chrom.size());
+            if (rc != BRC_OK) { std::fprintf(stderr, "brc_set_reference: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
+            ref_loaded.insert(g.tid);
+        }
+        brc_begin_region(eng, g.tid, g.beg, g.end, g.site_list ? 1 : 0);
+        // samfetch(in, idx, ref, d.beg-1, d.end): records with tid, endpos > max(beg-1,0), pos < end, in file order
+        const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
+        uint64_t voff;
+        if (bam.query_offset(g.tid, fbeg, voff) && bam.bz.seek(voff)) {
+            while (read_record(bam.bz, rec)) {
+                if (rec.tid != g.tid || rec.pos >= fend) break;
+                if (rec_endpos(rec) <= fbeg) continue;
+                uint16_t lib = 0;
+                if (per_lib) {
+                    lib = (uint16_t)BRC_LIB_NONE;
+                    if (rec.has_rg) { auto it = rg_lb.find(rec.rg); if (it != rg_lb.end()) lib = lib_rank[it->second]; }
+                }
+                rc = brc_push_read(eng, rec.tid, rec.pos, rec.flag, rec.mapq, lib, rec.l_qseq, rec.nm, rec.sm, rec.n_cigar, rec.cigar, rec.seq, rec.qual);
+                if (rc != BRC_OK) { std::fprintf(stderr, "brc_push_read: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
+                ++pushed;
+            }
+        }
+        brc_end_region(eng);
+        // site-list regions are independent: flush in batches; argv regions share the deletion queue -> one batch
+        if (g.site_list && (pushed > 4000000 || gi + 1 == regions.size())) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
+    }
+    if (!regions.empty() && !regions.back().site_list) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } }
+    int64_t w[4] = {0, 0, 0, 0};
+    (void)w;
+    brc_destroy(eng);
+    return 0;
+}

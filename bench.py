@@ -45,6 +45,19 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def profiled_traffic():
+    """DRAM bytes per K1 launch from the newest committed `ncu --set full` capture (profiles/traffic_*.json)."""
+    import glob
+    fs = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_*.json")))
+    if not fs:
+        return None, None
+    try:
+        d = json.load(open(fs[-1]))
+        return float(d["pileup_kernel"]["traffic"]), os.path.basename(fs[-1])
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -320,6 +333,7 @@ def our_arm(args):
         k1 = sum(k1_ms) / len(k1_ms)
         k0 = sum(k0_ms) / len(k0_ms)
         ach = alg_bytes / (k1 / 1000.0) / 1e9
+        traffic, traffic_src = profiled_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,7 +343,7 @@ def our_arm(args):
                        "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2; no flush" % (alg_bytes / 1e6),
                        "sharding": "one 10 Mb shard per GPU, no data-path collective", "gen_s": round(t_gen, 1)},
             "roofline": {"bound": "hbm", "kernel": "pileup_kernel (K1)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "k1_ms": k1, "k0_ms": k0,
                          "step_frac": alg_bytes / (ms_per_step / 1000.0) / 1e9 / peak},
             "gpu_launches": launches,

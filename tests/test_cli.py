@@ -1,0 +1,92 @@
+"""The C++ host `brc-readcount`: same command line and STDOUT as bam-readcount.
+CPU: flag handling that needs no device.  GPU: the reference's six integration-test command lines
+(R:integration-test/bam-readcount_test.py:29-116) against its golden files, through BGZF/BAM/BAI/FASTA
+decode -> C ABI -> CUDA kernels -> text emitter."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _cli():
+    from bam_readcount_b200 import build
+    build.build()
+    return build.build_cli()
+
+
+def test_cli_help_and_version_exit_code_1():
+    exe = _cli()
+    for flag in ("-h", "-v"):
+        p = subprocess.run([exe, flag], capture_output=True)
+        assert p.returncode == 1          # R:src/exe/bam-readcount/bamreadcount.cpp:467-475
+    p = subprocess.run([exe], capture_output=True)
+    assert p.returncode == 1 and b"Usage: bam-readcount" in p.stdout
+
+
+def _write_ref(tmp):
+    """ref.fa of contig 21: N everywhere except the window the fixture reads touch (stored in test_bam.npz)."""
+    z = np.load(os.path.join(GOLDEN, "test_bam.npz"))
+    L, wb = int(z["chrom_len"]), int(z["ref_win_beg"])
+    seq = np.full(L, ord("N"), dtype=np.uint8)
+    seq[wb:wb + z["ref_win"].shape[0]] = z["ref_win"]
+    from bam_readcount_b200 import synth
+    synth.write_fasta(os.path.join(tmp, "ref.fa"), "21", seq)
+    return os.path.join(tmp, "ref.fa")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,bam,golden", [
+    (["-w", "1", "-l", "site_list"], "test.bam", "expected_all_lib"),
+    (["-w", "1", "-p", "-l", "site_list"], "test.bam", "expected_per_lib"),
+    (["-w", "1", "-i", "-l", "site_list"], "test.bam", "expected_insertion_centric_all_lib"),
+    (["-w", "1", "-i", "-p", "-l", "site_list"], "test.bam", "expected_insertion_centric_per_lib"),
+    (["-w", "1", "REGIONS"], "test.bam", "expected_all_lib"),
+    (["-w", "1", "REGIONS"], "test_bad_rg.bam", "expected_all_lib"),
+])
+def test_cli_reproduces_reference_goldens(tmp_path, args, bam, golden):
+    exe = _cli()
+    ref = _write_ref(str(tmp_path))
+    argv = [exe, "-f", ref]
+    regions = []
+    for a in args:
+        if a == "REGIONS":
+            regions = ["21:10402985-10402985", "21:10405200-10405200"]
+        elif a == "site_list":
+            argv.append(os.path.join(GOLDEN, "site_list"))
+        else:
+            argv.append(a)
+    argv.append(os.path.join(GOLDEN, bam))
+    argv += regions
+    p = subprocess.run(argv, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout.decode("latin-1") == cases.load_golden_text(golden)
+    assert b"Minimum mapping quality is set to 0" in p.stderr
+
+
+@pytest.mark.gpu
+def test_cli_synthetic_bam_matches_oracle(tmp_path):
+    """A coordinate-sorted synthetic BAM (written with the samtools the oracle build leaves in oracle/_ref) through the
+    CLI, whole-contig region and a site list, against the CPU oracle."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import synth
+    exe = _cli()
+    case = cases.synthetic_case(L=40000, depth=30, seed=31, regions=((0, 1001, 38000),), site_list=False)
+    name, L, seq, _ = case["contigs"][0]
+    d = str(tmp_path)
+    synth.write_fasta(os.path.join(d, "ref.fa"), name, np.frombuffer(seq, dtype=np.uint8))
+    synth.write_sam(os.path.join(d, "s.sam"), case["batch"], [(name, L)])
+    subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-o", os.path.join(d, "s.bam"), os.path.join(d, "s.sam")])
+    subprocess.check_call([REF_SAMTOOLS, "index", os.path.join(d, "s.bam")])
+    for fl, argv in ((dict(min_mapq=20, min_bq=20), ["-q", "20", "-b", "20"]), (dict(per_lib=True, insertion_centric=True), ["-p", "-i"])):
+        want, _, _ = cases.run_oracle(case, fl, site_list=False)
+        p = subprocess.run([exe, "-w", "0", "-f", os.path.join(d, "ref.fa")] + argv + [os.path.join(d, "s.bam"), "chr1:1001-38000"], capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+        assert p.stdout.decode("latin-1") == want
