@@ -124,17 +124,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
         "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 // producer-side wait: long suspend-time hint so the idle producer lane does not burn issue slots
-template <uint32_t HINT_NS>
+// consumer-side wait: probe, then back off with nanosleep so a waiting warp does not steal issue slots from the
+// warps that share its scheduler (a bare try_wait loop re-issues every ~20 cycles)
+template <uint32_t SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAITH_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra DONEH_%=;\n"
-        "bra WAITH_%=;\n"
-        "DONEH_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(phase), "r"(HINT_NS) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(addr), "r"(phase) : "memory");
+        if (ok) return;
+        __nanosleep(SLEEP_NS);
+    }
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t phase) {
     asm volatile(
@@ -172,14 +177,33 @@ __device__ __forceinline__ uint32_t nib8(const uint8_t *base, int64_t t) {
     if (t & 1) x = (x << 4) | ((__byte_perm(w0, w1, sh + 4u) >> 4) & 0xFu);
     return x;
 }
+// same, from shared memory with 32-bit addressing (addr = byte address of symbol 0)
+__device__ __forceinline__ uint32_t nib8_smem(uint32_t addr, int t) {
+    const uint32_t a = addr + (uint32_t)(t >> 1);
+    const uint32_t sh = a & 3u, aw = a - sh;
+    uint32_t w0, w1;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(aw));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(aw + 4u));
+    const uint32_t sel = (sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12);
+    uint32_t x = __byte_perm(w0, w1, sel);
+    if (t & 1) x = (x << 4) | ((__byte_perm(w0, w1, sh + 4u) >> 4) & 0xFu);
+    return x;
+}
+__device__ __forceinline__ uint32_t lds_u8_k0(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t nib_nonzero(uint32_t v) { return (v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x11111111u; }
 
 constexpr int K0_READS = 128;
 constexpr int K0_SEQ_CAP = K0_READS * 80 + 32;
 constexpr int K0_QUAL_CAP = K0_READS * 160 + 32;
+constexpr int K0_REF_CAP = 4096;      // staged packed reference codes (8192 bases): the block's reads are position-sorted
 struct __align__(128) K0Smem {
     uint8_t seq[K0_SEQ_CAP];
     uint8_t qual[K0_QUAL_CAP];
+    uint8_t ref[K0_REF_CAP + 16];
     uint64_t bar;
 };
 
@@ -194,13 +218,25 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     const uint64_t qa = R.qual_off[r0] & ~15ull, qb = (R.qual_off[r1] + 15ull) & ~15ull;
     const uint64_t sa = R.seq_off[r0] & ~15ull, sb = (R.seq_off[r1] + 15ull) & ~15ull;
     const bool staged = (qb - qa) <= (uint64_t)K0_QUAL_CAP && (sb - sa) <= (uint64_t)K0_SEQ_CAP;
+    // single-region batches: the block's reads are position-sorted on one contig, so the reference codes they
+    // touch are one short window — stage it too (reads reaching past it fall back to global loads per op)
+    int64_t ra = 0, rb = 0;   // staged byte range of the packed reference, [ra, rb)
+    if (staged && P.n_regions == 1) {
+        const RefWin rw0 = P.refs[P.regions[0].tid_slot];
+        const int64_t p_first = (int64_t)R.pos[r0] - rw0.win_beg, p_last = (int64_t)R.pos[r1 - 1] - rw0.win_beg;
+        const int64_t nbytes = (rw0.win_len + 1) / 2 + 16;            // allocation is padded by >= 16 bytes of 'N'
+        ra = (p_first > 0 ? p_first >> 1 : 0) & ~15ll;
+        rb = min((((p_last + 1024) >> 1) + 31) & ~15ll, nbytes & ~15ll);
+        if (rb <= ra || rb - ra > K0_REF_CAP) { ra = rb = 0; }
+    }
     if (staged) {
         if (threadIdx.x == 0) {
             mbar_init(&ks.bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(&ks.bar, (uint32_t)(qb - qa) + (uint32_t)(sb - sa));
+            mbar_expect_tx(&ks.bar, (uint32_t)(qb - qa) + (uint32_t)(sb - sa) + (uint32_t)(rb - ra));
             tma_bulk_g2s(ks.qual, R.qual + qa, (uint32_t)(qb - qa), &ks.bar);
             tma_bulk_g2s(ks.seq, R.seq + sa, (uint32_t)(sb - sa), &ks.bar);
+            if (rb > ra) tma_bulk_g2s(ks.ref, reinterpret_cast<const uint8_t *>(P.refs[P.regions[0].tid_slot].seq) + ra, (uint32_t)(rb - ra), &ks.bar);
         }
         __syncthreads();   // barrier initialised before anyone waits on it
     }
@@ -223,6 +259,8 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     // generic pointers: shared memory when staged, the global pools otherwise (reads too long for the stage)
     const uint8_t *seq = staged ? (ks.seq + (soff - sa)) : (R.seq + soff);
     const uint8_t *qual = staged ? (ks.qual + (qoffb - qa)) : (R.qual + qoffb);
+    const uint32_t seq_sa = smem_u32(ks.seq) + (uint32_t)(soff - sa), qual_sa = smem_u32(ks.qual) + (uint32_t)(qoffb - qa);   // staged: 32-bit shared addresses
+    const uint32_t ref_sa = smem_u32(ks.ref) - (uint32_t)ra;
     const uint8_t *refc = reinterpret_cast<const uint8_t *>(rw.seq);   // packed 4-bit codes (launch_ref_encode)
 
     // --- fetch_func CIGAR/reference walk (R:...:133-199) + bam_cigar2rlen + SIMPLE detection ---
@@ -241,6 +279,7 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     bool in_m = false, hit_nul = false;
     int j = 0, jend = 0, m_len = 0;
     int64_t wrel = 0;
+    bool ref_staged = false;
     for (;;) {
         if (!in_m) {
             if (k >= n_cigar) break;
@@ -263,6 +302,8 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
                     wrel = reference_position - rw.win_beg;
                     j = wrel < 0 ? (int)min((int64_t)jn, -wrel) : 0;
                     jend = (int)max((int64_t)j, min((int64_t)jn, rw.win_len - wrel));
+                    // reference codes of this op: the staged window when it holds all of them (nib8 may read 8 bytes on)
+                    ref_staged = rb > ra && ((wrel + j) >> 1) >= ra && ((wrel + jend) >> 1) + 8 < rb;
                     m_len = op_length; in_m = true;
                 } else if (op == 2 || op == 3) reference_position += op_length;
                 else if (op == 1) read_position += op_length;
@@ -276,8 +317,8 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
         }
         if (j < jend) {
             // 8 bases per step: XOR of the packed read nibbles with the packed reference codes
-            const uint32_t X = nib8(seq, read_position + j);
-            const uint32_t Y = nib8(refc, wrel + j);
+            const uint32_t X = staged ? nib8_smem(seq_sa, read_position + j) : nib8(seq, read_position + j);
+            const uint32_t Y = ref_staged ? nib8_smem(ref_sa, (int)(wrel + j)) : nib8(refc, wrel + j);
             const uint32_t x = X ^ Y;
             if (x != 0u) {
                 const int nv = jend - j;
@@ -288,7 +329,7 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
                     const int k8 = __clz(m) >> 2;          // flag of symbol i sits at bit 28-4i
                     m &= ~(0x10000000u >> (4 * k8));
                     const int cur = read_position + j + k8;
-                    const int q = qual[cur];
+                    const int q = staged ? (int)lds_u8_k0(qual_sa + (uint32_t)cur) : (int)qual[cur];
                     if (last_mm_pos != -1) {
                         if (last_mm_pos + 1 != cur) { sum_mmq += (uint32_t)last_mm_qual; last_mm_qual = q; }
                         else if (last_mm_qual < q) last_mm_qual = q;
@@ -313,7 +354,7 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     if (reverse) { kk = tpi = 0; inc = 1; if (tpi < left_clip) tpi = left_clip; }
     else { kk = tpi = l_qseq - 1; inc = -1; if (tpi > right_clip) tpi = right_clip; }
     while (kk >= 0 && kk < l_qseq) {
-        if (qual[kk] != 2) { q2_pos = kk - 1; break; }
+        if ((staged ? lds_u8_k0(qual_sa + (uint32_t)kk) : (uint32_t)qual[kk]) != 2u) { q2_pos = kk - 1; break; }
         kk += inc;
     }
     if (reverse) { if (tpi < q2_pos) tpi = q2_pos; }
@@ -794,7 +835,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
 #ifdef BRC_K1_PROFILE
         const long long tc0 = clock64();
 #endif
-        mbar_wait_hint<2000>(&sm.full[s], ph);
+        mbar_wait_hint<200>(&sm.full[s], ph);
 #ifdef BRC_K1_PROFILE
         const long long tc1 = clock64();
 #endif
