@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include <zlib.h>
+#include <chrono>
 
 #include "../../include/brc_engine.h"
 
@@ -390,25 +391,55 @@ int main(int argc, char **argv) {
     std::set<int> ref_loaded;
     std::string chrom;
     Rec rec;
+    const bool timing = std::getenv("BRC_CLI_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_decode = 0, t_compute = 0, t_format = 0, t_write = 0, t_ref = 0;
     auto flush = [&]() -> int {
+        const double c0 = now();
         int r = brc_compute(eng);
+        t_compute += now() - c0;
         if (r != BRC_OK) { std::fprintf(stderr, "brc_compute: %s\n", brc_last_error(eng)); return r; }
-        const int64_t need = brc_format_text(eng, -1, lib_ptrs.data(), nullptr, 0);
-        if (need < 0) { std::fprintf(stderr, "brc_format_text: %s\n", brc_last_error(eng)); return (int)need; }
-        std::vector<char> out((size_t)need + 1);
-        brc_format_text(eng, -1, lib_ptrs.data(), out.data(), need + 1);
-        std::fwrite(out.data(), 1, (size_t)need, stdout);
+        brc_results res{};
+        if ((r = brc_get_results(eng, &res)) != BRC_OK) { std::fprintf(stderr, "brc_get_results: %s\n", brc_last_error(eng)); return r; }
+        std::vector<char> out;
+        auto emit = [&](int64_t need, auto &&fill) -> int {
+            if (need < 0) { std::fprintf(stderr, "format: %s\n", brc_last_error(eng)); return (int)need; }
+            out.resize((size_t)need + 1);
+            fill(out.data(), need + 1);
+            const double w0 = now();
+            std::fwrite(out.data(), 1, (size_t)need, stdout);
+            t_write += now() - w0;
+            return BRC_OK;
+        };
+        const double f0 = now();
+        const bool argv_chain = res.n_regions > 1 && !res.regions[0].site_list_mode;   // never-cleared deletion queue: one sequential pass
+        if (argv_chain) {
+            const int64_t need = brc_format_text(eng, -1, lib_ptrs.data(), nullptr, 0);
+            if (emit(need, [&](char *b, int64_t c) { brc_format_text(eng, -1, lib_ptrs.data(), b, c); }) != BRC_OK) return -1;
+        } else {
+            const int64_t WIN = 1 << 21;   // stream big regions in 2M-site windows (each formatted by several threads)
+            for (int64_t g = 0; g < res.n_regions; ++g)
+                for (int64_t first = 0; first < res.regions[g].n_slots; first += WIN) {
+                    const int64_t need = brc_format_window(eng, g, first, WIN, lib_ptrs.data(), nullptr, 0);
+                    if (need == 0) continue;
+                    if (emit(need, [&](char *b, int64_t c) { brc_format_window(eng, g, first, WIN, lib_ptrs.data(), b, c); }) != BRC_OK) return -1;
+                }
+        }
+        t_format += now() - f0;
         return brc_reset(eng);
     };
     int64_t pushed = 0;
     for (size_t gi = 0; gi < regions.size(); ++gi) {
         const Region &g = regions[gi];
+        const double d0 = now();
         if (!ref_loaded.count(g.tid)) {   // load_reference: whole chromosome
             if (!fa.fetch(bam.names[(size_t)g.tid], chrom)) { std::fprintf(stderr, "Failed to fetch %s from %s\n", bam.names[(size_t)g.tid].c_str(), fn_fa.c_str()); brc_destroy(eng); return 1; }
             rc = brc_set_reference(eng, g.tid, bam.names[(size_t)g.tid].c_str(), (int64_t)chrom.size(), 0, chrom.data(), (int64_t)chrom.size());
             if (rc != BRC_OK) { std::fprintf(stderr, "brc_set_reference: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
             ref_loaded.insert(g.tid);
+            t_ref += now() - d0;
         }
+        const double d1 = now();
         brc_begin_region(eng, g.tid, g.beg, g.end, g.site_list ? 1 : 0);
         // samfetch(in, idx, ref, d.beg-1, d.end): records with tid, endpos > max(beg-1,0), pos < end, in file order
         const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
@@ -428,12 +459,12 @@ int main(int argc, char **argv) {
             }
         }
         brc_end_region(eng);
+        t_decode += now() - d1;
         // site-list regions are independent: flush in batches; argv regions share the deletion queue -> one batch
         if (g.site_list && (pushed > 4000000 || gi + 1 == regions.size())) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
     }
     if (!regions.empty() && !regions.back().site_list) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } }
-    int64_t w[4] = {0, 0, 0, 0};
-    (void)w;
+    if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
     brc_destroy(eng);
     return 0;
 }

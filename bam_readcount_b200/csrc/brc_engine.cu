@@ -461,7 +461,7 @@ static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetch
         }
     }
     e->warn_counts[3] = lu;
-    e->results_valid = true;
+    e->results_valid = true; e->fmt_valid = false;
     return BRC_OK;
 }
 

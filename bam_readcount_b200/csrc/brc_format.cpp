@@ -6,24 +6,29 @@
 //   IndelQueue::process              R:src/lib/bamrc/IndelQueue.cpp:3-15
 //
 // Only formatting, ordering of allele strings and the p -> p+1 deletion shift live here; every
-// number printed was accumulated on the GPU.  Averages are float32 divisions printed with
-// "%.2f" of the value promoted to double, exactly like `std::fixed << setprecision(2)`.
+// number printed was accumulated on the GPU.  Averages are float32 divisions printed exactly like
+// `std::fixed << setprecision(2)` == printf("%.2f", (double)f): `put_f2` rounds the exact binary value
+// half-to-even in integer arithmetic (no printf in the hot path); a region is formatted by several
+// threads over disjoint site ranges — the deletion shift only needs the site to the left, which each
+// thread re-derives for its first site.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "brc_engine_internal.h"
+#include "brc_fmt_num.h"
 
 namespace {
 
 struct Stat { uint32_t v[BRC_N_STATS]; };
 inline float f32(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
-void put_f2(std::string &o, float x) { char t[64]; int n = std::snprintf(t, sizeof t, "%.2f", (double)x); o.append(t, (size_t)n); }
-void put_u(std::string &o, uint32_t x) { char t[16]; int n = std::snprintf(t, sizeof t, "%u", x); o.append(t, (size_t)n); }
+using brc::put_u;
+using brc::put_f2;
 
 // operator<<(std::ostream&, const BasicStat&)
 void put_stat(std::string &o, const Stat *s, bool is_indel) {
@@ -57,84 +62,148 @@ struct EmitState {
 const char kNt[] = "=ACGTN";
 const uint8_t kCanon[16] = {0, 1, 2, 5, 3, 5, 5, 5, 4, 5, 5, 5, 5, 5, 5, 5};
 
-void format_region(const brc_engine *e, int64_t g, const char *const *lib_names, EmitState &st, std::string &out) {
-    const brc_region &rg = e->regions[(size_t)g];
-    const brc::HostRef *ref = brc::find_ref(e, rg.tid);
-    const int rows = e->n_rows;
-    const int64_t NS = e->n_slots, RS = (int64_t)rows * NS;
-    const uint32_t *ncover = e->h_ncover.as<uint32_t>(), *npass = e->h_npass.as<uint32_t>(), *pstats = e->h_pstats.as<uint32_t>();
-    const uint8_t *flags = e->h_flags.as<uint8_t>(), *pbase = e->h_pbase.as<uint8_t>(), *skind = e->h_sec_kind.as<uint8_t>();
-    const int32_t *shead = e->h_sec_head.as<int32_t>(), *snext = e->h_sec_next.as<int32_t>(), *slen = e->h_sec_len.as<int32_t>(),
-                  *sqpos = e->h_sec_qpos.as<int32_t>();
-    const int64_t *sread = e->h_sec_read.as<int64_t>();
-    const uint32_t *sstats = e->h_sec_stats.as<uint32_t>();
-    const int64_t SC = e->h_sec_cap;
-    const uint8_t *h_seq = e->host_seq(); const uint64_t *h_seq_off = e->host_seq_off();
-    std::string rec;
-    struct Indel { std::string allele; Stat st; };
-    std::vector<Indel> indels;
-    for (int32_t s = 0; s < rg.n_slots; ++s) {
-        const int64_t slot = rg.slot_base + s;
-        const int64_t pos = (int64_t)rg.first_pos + s;
-        uint64_t n_total = 0, mapq_n = 0; bool abandoned = false;
-        for (int r = 0; r < rows; ++r) { n_total += ncover[r * NS + slot]; mapq_n += npass[r * NS + slot]; abandoned |= (flags[r * NS + slot] & 1) != 0; }
-        if (n_total == 0 && !abandoned) continue;       // no read spans the site: the callback never fires
-        if (abandoned) continue;                        // -p and a read without library: `return 0` before anything is kept
-        rec.clear();
-        int64_t extra_depth = 0;
-        for (int r = 0; r < rows; ++r) {
-            const int64_t idx = r * NS + slot;
-            if (ncover[idx] == 0) continue;
-            if (e->cfg.per_lib) { rec += '\t'; rec += lib_names ? lib_names[r] : "?"; rec += "\t{"; }
-            Stat base[6]; bool have[6] = {false, false, false, false, false, false};
-            indels.clear();
-            if (pbase[idx] < 6) { for (int k = 0; k < BRC_N_STATS; ++k) base[pbase[idx]].v[k] = pstats[(int64_t)k * RS + idx]; have[pbase[idx]] = true; }
-            for (int32_t j = shead[idx]; j >= 0; j = snext[j]) {
-                Stat t; for (int k = 0; k < BRC_N_STATS; ++k) t.v[k] = sstats[(int64_t)k * SC + j];
-                if (skind[j] < 6) { base[skind[j]] = t; have[skind[j]] = true; continue; }
-                Indel in; in.st = t;
-                if (skind[j] == BRC_KIND_INS) {          // "+" + canonicalised read bases qpos+1..qpos+len  (R:...:324-330)
-                    in.allele = "+";
-                    const uint8_t *sq = h_seq + h_seq_off[(size_t)sread[j]];
-                    for (int k = 1; k <= slen[j]; ++k) { int i = sqpos[j] + k; uint8_t b = sq[i >> 1]; in.allele += kNt[kCanon[(i & 1) ? (b & 15) : (b >> 4)]]; }
-                } else {                                 // "-" + raw reference characters pos+1..pos+len (R:...:331-339)
-                    in.allele = "-";
-                    for (int k = 1; k <= slen[j]; ++k) {
-                        int64_t p = pos + k; char c = 'N';
-                        if (ref && p >= ref->win_beg && p < ref->win_beg + ref->win_len && p < ref->chrom_len) c = ref->seq[(size_t)(p - ref->win_beg)];
-                        in.allele += c;
-                    }
-                }
-                indels.push_back(std::move(in));
-            }
-            for (int j = 0; j < 6; ++j) { rec += '\t'; rec += kNt[j]; rec += ':'; put_stat(rec, have[j] ? &base[j] : nullptr, false); }
-            std::sort(indels.begin(), indels.end(), [](const Indel &a, const Indel &b) { return a.allele < b.allele; });
-            for (auto &in : indels) {
-                if (in.allele[0] == '-') { st.q[(size_t)r].push_back(QEnt{rg.tid, pos + 1, in.st, in.allele}); st.q_exists[(size_t)r] = 1; }
-                else { rec += '\t'; rec += in.allele; rec += ':'; put_stat(rec, &in.st, true); }
-            }
-            if (st.q_exists[(size_t)r]) {               // IndelQueue::process(tid, pos, record)
-                auto &q = st.q[(size_t)r];
-                while (!q.empty() && ((q.front().tid == rg.tid && q.front().pos < pos) || q.front().tid != rg.tid)) q.pop_front();
-                while (!q.empty() && q.front().tid == rg.tid && q.front().pos == pos) {
-                    rec += '\t'; rec += q.front().allele; rec += ':'; put_stat(rec, &q.front().st, true);
-                    extra_depth += q.front().st.v[BRC_S_COUNT];
-                    q.pop_front();
-                }
-            }
-            if (e->cfg.per_lib) rec += "\t}";
-        }
-        if (pos >= rg.beg && pos < rg.end) {
-            char rb = 'N';
-            if (ref && pos < ref->chrom_len && pos >= ref->win_beg && pos < ref->win_beg + ref->win_len) rb = ref->seq[(size_t)(pos - ref->win_beg)];
-            out += ref ? ref->name : std::string("?"); out += '\t';
-            char t[32]; int n = std::snprintf(t, sizeof t, "%lld", (long long)(pos + 1)); out.append(t, (size_t)n);
-            out += '\t'; out += rb; out += '\t';
-            n = std::snprintf(t, sizeof t, "%lld", (long long)((int64_t)mapq_n + extra_depth)); out.append(t, (size_t)n);
-            out += rec; out += '\n';
-        }
+struct View {   // raw result arrays of one engine
+    const brc_engine *e; const brc_region *rg; const brc::HostRef *ref;
+    int rows; int64_t NS, RS, SC;
+    const uint32_t *ncover, *npass, *pstats, *sstats; const uint8_t *flags, *pbase, *skind;
+    const int32_t *shead, *snext, *slen, *sqpos; const int64_t *sread;
+    const uint8_t *h_seq; const uint64_t *h_seq_off;
+    View(const brc_engine *en, int64_t g) : e(en), rg(&en->regions[(size_t)g]), ref(brc::find_ref(en, rg->tid)) {
+        rows = e->n_rows; NS = e->n_slots; RS = (int64_t)rows * NS; SC = e->h_sec_cap;
+        ncover = e->h_ncover.as<uint32_t>(); npass = e->h_npass.as<uint32_t>(); pstats = e->h_pstats.as<uint32_t>(); sstats = e->h_sec_stats.as<uint32_t>();
+        flags = e->h_flags.as<uint8_t>(); pbase = e->h_pbase.as<uint8_t>(); skind = e->h_sec_kind.as<uint8_t>();
+        shead = e->h_sec_head.as<int32_t>(); snext = e->h_sec_next.as<int32_t>(); slen = e->h_sec_len.as<int32_t>(); sqpos = e->h_sec_qpos.as<int32_t>();
+        sread = e->h_sec_read.as<int64_t>(); h_seq = e->host_seq(); h_seq_off = e->host_seq_off();
     }
-    if (rg.site_list_mode) st.clear();                  // d.indel_queue_map.clear()  (R:...:605)
+};
+
+struct Indel { std::string allele; Stat st; };
+struct Scratch { std::string rec; std::vector<Indel> indels; };
+
+// One site: pileup_func's print section.  emit=false only replays the deletion pushes (used to seed a thread's first site).
+void format_site(const View &V, int32_t s, const char *const *lib_names, EmitState &st, std::string &out, Scratch &W, bool emit) {
+    const brc_region &rg = *V.rg;
+    const int rows = V.rows; const int64_t NS = V.NS;
+    const int64_t slot = rg.slot_base + s;
+    const int64_t pos = (int64_t)rg.first_pos + s;
+    uint64_t n_total = 0, mapq_n = 0; bool abandoned = false;
+    for (int r = 0; r < rows; ++r) { n_total += V.ncover[r * NS + slot]; mapq_n += V.npass[r * NS + slot]; abandoned |= (V.flags[r * NS + slot] & 1) != 0; }
+    if (n_total == 0 || abandoned) return;   // no callback / -p with a read lacking a library: `return 0` before anything is kept
+    std::string &rec = W.rec; rec.clear();
+    int64_t extra_depth = 0;
+    for (int r = 0; r < rows; ++r) {
+        const int64_t idx = r * NS + slot;
+        if (V.ncover[idx] == 0) continue;
+        if (emit && V.e->cfg.per_lib) { rec += '\t'; rec += lib_names ? lib_names[r] : "?"; rec += "\t{"; }
+        Stat base[6]; bool have[6] = {false, false, false, false, false, false};
+        W.indels.clear();
+        if (V.pbase[idx] < 6) { for (int k = 0; k < BRC_N_STATS; ++k) base[V.pbase[idx]].v[k] = V.pstats[(int64_t)k * V.RS + idx]; have[V.pbase[idx]] = true; }
+        for (int32_t j = V.shead[idx]; j >= 0; j = V.snext[j]) {
+            Stat t; for (int k = 0; k < BRC_N_STATS; ++k) t.v[k] = V.sstats[(int64_t)k * V.SC + j];
+            if (V.skind[j] < 6) { base[V.skind[j]] = t; have[V.skind[j]] = true; continue; }
+            Indel in; in.st = t;
+            if (V.skind[j] == BRC_KIND_INS) {          // "+" + canonicalised read bases qpos+1..qpos+len  (R:...:324-330)
+                in.allele = "+";
+                const uint8_t *sq = V.h_seq + V.h_seq_off[(size_t)V.sread[j]];
+                for (int k = 1; k <= V.slen[j]; ++k) { int i = V.sqpos[j] + k; uint8_t b = sq[i >> 1]; in.allele += kNt[kCanon[(i & 1) ? (b & 15) : (b >> 4)]]; }
+            } else {                                   // "-" + raw reference characters pos+1..pos+len (R:...:331-339)
+                in.allele = "-";
+                for (int k = 1; k <= V.slen[j]; ++k) {
+                    int64_t p = pos + k; char c = 'N';
+                    if (V.ref && p >= V.ref->win_beg && p < V.ref->win_beg + V.ref->win_len && p < V.ref->chrom_len) c = V.ref->seq[(size_t)(p - V.ref->win_beg)];
+                    in.allele += c;
+                }
+            }
+            W.indels.push_back(std::move(in));
+        }
+        if (emit) for (int j = 0; j < 6; ++j) { rec += '\t'; rec += kNt[j]; rec += ':'; put_stat(rec, have[j] ? &base[j] : nullptr, false); }
+        if (W.indels.size() > 1) std::sort(W.indels.begin(), W.indels.end(), [](const Indel &a, const Indel &b) { return a.allele < b.allele; });
+        for (auto &in : W.indels) {
+            if (in.allele[0] == '-') { st.q[(size_t)r].push_back(QEnt{rg.tid, pos + 1, in.st, in.allele}); st.q_exists[(size_t)r] = 1; }
+            else if (emit) { rec += '\t'; rec += in.allele; rec += ':'; put_stat(rec, &in.st, true); }
+        }
+        if (emit && st.q_exists[(size_t)r]) {          // IndelQueue::process(tid, pos, record)
+            auto &q = st.q[(size_t)r];
+            while (!q.empty() && ((q.front().tid == rg.tid && q.front().pos < pos) || q.front().tid != rg.tid)) q.pop_front();
+            while (!q.empty() && q.front().tid == rg.tid && q.front().pos == pos) {
+                rec += '\t'; rec += q.front().allele; rec += ':'; put_stat(rec, &q.front().st, true);
+                extra_depth += q.front().st.v[BRC_S_COUNT];
+                q.pop_front();
+            }
+        }
+        if (emit && V.e->cfg.per_lib) rec += "\t}";
+    }
+    if (emit && pos >= rg.beg && pos < rg.end) {
+        char rb = 'N';
+        if (V.ref && pos < V.ref->chrom_len && pos >= V.ref->win_beg && pos < V.ref->win_beg + V.ref->win_len) rb = V.ref->seq[(size_t)(pos - V.ref->win_beg)];
+        if (V.ref) out += V.ref->name; else out += '?';
+        out += '\t'; put_u(out, (uint64_t)(pos + 1)); out += '\t'; out += rb; out += '\t';
+        put_u(out, (uint64_t)((int64_t)mapq_n + extra_depth));
+        out += rec; out += '\n';
+    }
+}
+
+// sites [s0, s1) of region g, sequentially, with the caller's queue state
+void format_range(const View &V, int32_t s0, int32_t s1, const char *const *lib_names, EmitState &st, std::string &out) {
+    Scratch W;
+    for (int32_t s = s0; s < s1; ++s) format_site(V, s, lib_names, st, out, W, true);
+}
+
+void format_region(const brc_engine *e, int64_t g, int32_t s0, int32_t s1, const char *const *lib_names, EmitState &st, std::string &out, bool seed_from_left) {
+    const View V(e, g);
+    const brc_region &rg = *V.rg;
+    s0 = std::max(s0, 0); s1 = std::min(s1, rg.n_slots);
+    if (s1 <= s0) { if (rg.site_list_mode && s1 >= rg.n_slots) st.clear(); return; }
+    const int32_t n = s1 - s0;
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<int64_t>({(int64_t)(hw ? hw : 1), (int64_t)32, (int64_t)n / 16384 + 1});
+    // The deletion queue carries state across sites.  Inside one region only the site to the left matters, so ranges can be
+    // formatted independently — except in the argv loop with several regions, whose queue is never cleared (A.6): keep that sequential.
+    if (!rg.site_list_mode && e->regions.size() > 1) nt = 1;
+    if (nt <= 1) {
+        if (seed_from_left && s0 > 0) { Scratch W; std::string sink; format_site(V, s0 - 1, lib_names, st, sink, W, false); }
+        format_range(V, s0, s1, lib_names, st, out);
+    } else {
+        std::vector<std::string> parts((size_t)nt);
+        std::vector<EmitState> states; states.reserve((size_t)nt);
+        for (int t = 0; t < nt; ++t) states.emplace_back(e->n_rows);
+        auto work = [&](int t) {
+            const int32_t a = s0 + (int32_t)((int64_t)n * t / nt), b = s0 + (int32_t)((int64_t)n * (t + 1) / nt);
+            EmitState &ls = t == 0 ? st : states[(size_t)t];
+            parts[(size_t)t].reserve((size_t)(b - a) * 420);
+            if ((t > 0 || seed_from_left) && a > 0) { Scratch W; std::string sink; format_site(V, a - 1, lib_names, ls, sink, W, false); }
+            format_range(V, a, b, lib_names, ls, parts[(size_t)t]);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+        size_t tot = out.size(); for (auto &p : parts) tot += p.size();
+        out.reserve(tot);
+        for (auto &p : parts) out += p;
+        if (nt > 1) { st.clear(); for (size_t r = 0; r < st.q.size(); ++r) { st.q[r] = states[(size_t)nt - 1].q[r]; st.q_exists[r] = states[(size_t)nt - 1].q_exists[r]; } }
+    }
+    if (rg.site_list_mode && s1 >= rg.n_slots) st.clear();                  // d.indel_queue_map.clear()  (R:...:605)
+}
+
+// the caller's usual pattern is a size query (buf == NULL) followed by the fill: format once, keep the text
+int64_t serve(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const char *const *lib_names, char *buf, int64_t cap) {
+    if (!(e->fmt_valid && e->fmt_key[0] == k0 && e->fmt_key[1] == k1 && e->fmt_key[2] == k2)) {
+        e->fmt_cache.clear();
+        EmitState st(e->n_rows);
+        if (k1 == -1) {   // whole regions
+            if (k0 < 0) for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, 0, e->regions[(size_t)g].n_slots, lib_names, st, e->fmt_cache, false);
+            else format_region(e, k0, 0, e->regions[(size_t)k0].n_slots, lib_names, st, e->fmt_cache, false);
+        } else format_region(e, k0, (int32_t)k1, (int32_t)std::min<int64_t>(k1 + k2, 0x7fffffff), lib_names, st, e->fmt_cache, true);
+        e->fmt_key[0] = k0; e->fmt_key[1] = k1; e->fmt_key[2] = k2; e->fmt_valid = true;
+    }
+    const int64_t n = (int64_t)e->fmt_cache.size();
+    if (buf && cap > 0) {
+        const int64_t c = std::min<int64_t>(n, cap - 1);
+        std::memcpy(buf, e->fmt_cache.data(), (size_t)c); buf[c] = 0;
+        e->fmt_valid = false; std::string().swap(e->fmt_cache);   // delivered: release the memory
+    }
+    return n;
 }
 
 }  // namespace
@@ -144,13 +213,14 @@ extern "C" int64_t brc_format_text(brc_engine *e, int64_t region_index, const ch
     if (!e->results_valid) return brc::set_error(e, BRC_E_INVALID, "format_text: no results");
     if (e->n_host_reads() == 0 && e->h_n_sec > 0) return brc::set_error(e, BRC_E_INVALID, "format_text: needs the pushed reads (push path only)");
     if (region_index >= (int64_t)e->regions.size()) return BRC_E_INVALID;
-    std::string out;
-    EmitState st(e->n_rows);
-    if (region_index < 0) for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, lib_names, st, out);
-    else format_region(e, region_index, lib_names, st, out);
-    if (buf && cap > 0) {
-        int64_t n = std::min<int64_t>((int64_t)out.size(), cap - 1);
-        std::memcpy(buf, out.data(), (size_t)n); buf[n] = 0;
-    }
-    return (int64_t)out.size();
+    return serve(e, region_index < 0 ? -1 : region_index, -1, -1, lib_names, buf, cap);
+}
+
+// A window of one region's sites (slot offsets [first, first+count) inside the region), for callers that stream the text
+// of a large region piecewise.  The deletion columns of the window's first site are re-derived from the site to its left.
+extern "C" int64_t brc_format_window(brc_engine *e, int64_t region_index, int64_t first, int64_t count, const char *const *lib_names,
+                                     char *buf, int64_t cap) {
+    if (!e || region_index < 0 || region_index >= (int64_t)e->regions.size() || first < 0 || count < 0) return BRC_E_INVALID;
+    if (!e->results_valid) return brc::set_error(e, BRC_E_INVALID, "format_window: no results");
+    return serve(e, region_index, first, count, lib_names, buf, cap);
 }

@@ -201,6 +201,12 @@ BRC_API int brc_get_warning_counts(brc_engine *e, int64_t out[4]);
  * Returns the number of bytes required (excluding NUL); writes at most cap-1 bytes + NUL. */
 BRC_API int64_t brc_format_text(brc_engine *e, int64_t region_index, const char *const *lib_names, char *buf, int64_t cap);
 
+/* Same, for a window of one region's sites: slot offsets [first, first+count) inside region `region_index` (site
+ * first_pos+first onwards).  Lets a caller stream the text of a large region piecewise; the window's first site
+ * re-derives its deletion columns from the site to its left.  Formatting runs on several host threads. */
+BRC_API int64_t brc_format_window(brc_engine *e, int64_t region_index, int64_t first, int64_t count, const char *const *lib_names,
+                                  char *buf, int64_t cap);
+
 /* ---- device-resident path (bench "value": inputs already in HBM) -------------------------
  * brc_plan_device: fix the region geometry (host array of n_regions regions with read_lo/hi,
  * slot_base, first_pos, n_slots filled) and size the outputs.  brc_run_device: launch the
