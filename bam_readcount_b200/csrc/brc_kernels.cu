@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
         soff = R.seq_off[i]; qoffb = R.qual_off[i];
     }
     if (staged) mbar_wait(&ks.bar, 0);
+    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
     if (!live) return;
     const uint32_t *cig = R.cigar + coff;
     // generic pointers: shared memory when staged, the global pools otherwise (reads too long for the stage)
@@ -394,13 +395,22 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     for (int q = 0; q < 5; ++q) dst[q] = src[q];
 
     // --- which tiles of this read's region does it overlap?  (first/last read per tile) ---
+    // Lanes of a warp hold consecutive reads, so a tile's smallest read index comes from the lowest lane touching
+    // it and the largest from the highest: a lane skips the atomic when its neighbour covers the same tile
+    // (32x fewer same-address atomics on deep sites).
     int64_t a = pos > rg.first_pos ? pos : rg.first_pos;
     int64_t b = end < rg.end ? end : rg.end;
-    if (b > a) {
-        int64_t t0 = rg.tile_base + (a - rg.first_pos) / TILE;
-        int64_t t1 = rg.tile_base + (b - 1 - rg.first_pos) / TILE;
-        const int32_t idx = (int32_t)i;
-        for (int64_t t = t0; t <= t1; ++t) { atomicMin(P.tile_lo + t, idx); atomicMax(P.tile_hi + t, idx + 1); }
+    const bool has = b > a;
+    const int64_t t0 = has ? rg.tile_base + (a - rg.first_pos) / TILE : 1;
+    const int64_t t1 = has ? rg.tile_base + (b - 1 - rg.first_pos) / TILE : 0;    // empty range when !has
+    const int lane = threadIdx.x & 31;
+    const int64_t p0 = __shfl_up_sync(live_mask, t0, 1), p1 = __shfl_up_sync(live_mask, t1, 1);
+    const int64_t n0 = __shfl_down_sync(live_mask, t0, 1), n1 = __shfl_down_sync(live_mask, t1, 1);
+    const bool has_prev = lane > 0, has_next = lane < 31 && ((live_mask >> (lane + 1)) & 1u);
+    const int32_t idx = (int32_t)i;
+    for (int64_t t = t0; t <= t1; ++t) {
+        if (!(has_prev && p0 <= t && t <= p1)) atomicMin(P.tile_lo + t, idx);
+        if (!(has_next && n0 <= t && t <= n1)) atomicMax(P.tile_hi + t, idx + 1);
     }
 }
 
@@ -579,6 +589,7 @@ struct __align__(128) StageBuf {
 struct __align__(128) PileupSmem {
     StageBuf st[NSTAGE];
     uint32_t sacc[N_STATS][TILE];   // second base class of each site (stat-major: conflict-free)
+    uint32_t warn[2][TILE];         // per-thread warning counters (NM missing, SM missing): off the register file
     ChunkInfo info[NSTAGE];
     uint64_t full[NSTAGE], empty[NSTAGE];
 };
@@ -594,27 +605,38 @@ struct SiteState {
     Acc acc;
     uint32_t ncover, npass, flags, pbase, sbase;
     int32_t sec_head;
-    uint32_t warn_sm = 0, warn_nm = 0;
     bool warp_done;
     int32_t site;      // -1 for lanes beyond the tile's last site (never covered: positions are >= 0)
     int32_t wfirst;    // first site of this warp; the warp's window is [wfirst, wfirst+31]
+    uint32_t row;      // library row this thread accumulates
 };
-__device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci, int tid) {
+template <bool PER_LIB>
+__device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci, int tid, int n_rows) {
     Acc &a = S.acc;
     a.count = a.mapq = a.baseq = a.se = a.plus = a.mmqs = a.nq2 = a.clip = 0;
     a.nmf = a.q2d = a.d3p = 0.0f; a.posd = 0.0;
-    S.ncover = S.npass = S.flags = 0; S.pbase = S.sbase = NO_BASE; S.sec_head = -1;
-    S.site = tid < ci.n ? ci.pos0 + tid : -1;
-    S.wfirst = ci.pos0 + (tid & ~31);
-    S.warp_done = (tid & ~31) >= ci.n;
+    S.ncover = S.npass = 0; if (PER_LIB) S.flags = 0; S.pbase = S.sbase = NO_BASE; S.sec_head = -1;
+    if (PER_LIB && (ci.flags & 8u)) {   // narrow tile: warp = library row, lane = site
+        const int lane = tid & 31;
+        S.row = ci.row + (uint32_t)(tid >> 5);
+        const bool ok = S.row < (uint32_t)n_rows && lane < ci.n;
+        S.site = ok ? ci.pos0 + lane : -1;
+        S.wfirst = ci.pos0;
+        S.warp_done = S.row >= (uint32_t)n_rows;
+    } else {
+        S.row = PER_LIB ? ci.row : 0u;
+        S.site = tid < ci.n ? ci.pos0 + tid : -1;
+        S.wfirst = ci.pos0 + (tid & ~31);
+        S.warp_done = (tid & ~31) >= ci.n;
+    }
 }
 
 __device__ __forceinline__ int2 lds_i2(const void *p) { return *reinterpret_cast<const int2 *>(p); }
 
 // The hot loop: one warp walks the chunk's reads in file order; lane = site.
 template <bool PER_LIB, bool STAGED>
-__device__ __forceinline__ void process_chunk(const PileupParams &P, const StageBuf &sb, uint32_t (*sacc)[TILE], const ChunkInfo &ci,
-                                              SiteState &S, int tid) {
+__device__ __forceinline__ void process_chunk(const PileupParams &P, const StageBuf &sb, uint32_t (*sacc)[TILE], uint32_t (*warn)[TILE],
+                                              const ChunkInfo &ci, SiteState &S, int tid) {
     const int4 *ds = sb.desc;
     const int4 *const ds_end = ds + (ci.r1 - ci.r0) * 5;
     const uint32_t qual_s = smem_u32(sb.qual) - ci.qbase32;   // staged bytes are addressed with the reads' low-32 pool offsets
@@ -644,7 +666,7 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         if (PER_LIB) {
             const uint32_t lib = (uint32_t)fl2.y & 0xFFFFu;
             if (lib == LIB_NONE) { if (cover) S.flags |= 1u; continue; }
-            if (lib != ci.row) continue;
+            if (lib != S.row) continue;
             // -p: pileup_func returns at the first read without a library (R:...:281-284); nothing after
             // it in pileup (= file) order is processed or warned about at this site
             if (S.flags & 1u) continue;
@@ -672,10 +694,10 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         if (indel != 0) {
             const int32_t r = ci.r0 + (int)((ds - sb.desc) / 5);
             S.sec_head = rare_event(P, S.sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
-            if (warns) { S.warn_nm += (fm >> 25) & 1u; S.warn_sm += (fm >> 26) & 1u; }
+            if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
             if (indel > 0 && P.insertion_centric) continue;
         }
-        if (warns) { S.warn_nm += (fm >> 25) & 1u; S.warn_sm += (fm >> 26) & 1u; }
+        if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
         uint32_t byte;
         if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
         else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
@@ -722,8 +744,9 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
 }
 
 // last chunk of a tile: write the site's header + primary accumulators (coalesced SoA stores)
+template <bool PER_LIB>
 __device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc)[TILE], const ChunkInfo &ci, SiteState &S, int tid) {
-    if (tid >= ci.n) return;
+    if (S.site < 0) return;
     const ResultsDev &R = P.res;
     int32_t sec_head = S.sec_head;
     if (S.sbase != NO_BASE) {   // move the second base class into the record pool
@@ -735,10 +758,10 @@ __device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc
             sec_head = j;
         }
     }
-    const int64_t idx = (int64_t)ci.row * R.n_slots + ci.slot0 + tid;
+    const int64_t idx = (PER_LIB ? (int64_t)S.row * R.n_slots : 0) + ci.slot0 + (S.site - ci.pos0);
     const int64_t stride = (int64_t)R.n_rows * R.n_slots;
     const Acc &a = S.acc;
-    R.ncover[idx] = S.ncover; R.npass[idx] = S.npass; R.flags[idx] = (uint8_t)S.flags; R.pbase[idx] = (uint8_t)S.pbase;
+    R.ncover[idx] = S.ncover; R.npass[idx] = S.npass; R.flags[idx] = (uint8_t)(PER_LIB ? S.flags : 0u); R.pbase[idx] = (uint8_t)S.pbase;
     R.sec_head[idx] = sec_head;
     uint32_t *ps = R.pstats + idx;
     ps[0 * stride] = a.count; ps[1 * stride] = a.mapq; ps[2 * stride] = a.baseq; ps[3 * stride] = a.se;
@@ -768,10 +791,15 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
         for (int64_t w = blockIdx.x;; w += gridDim.x) {
             const bool done = w >= n_work;
             int32_t lo = 0, hi = 0; TileInfo ti{0, 0, 0}; uint32_t row = 0;
+            bool narrow = false;
             if (!done) {
                 const int64_t tile = P.tile_begin + w % P.tile_count; row = (uint32_t)(w / P.tile_count);
                 ti = P.tiles[tile]; lo = P.tile_lo[tile]; hi = P.tile_hi[tile];
                 if (lo >= hi) { lo = 0; hi = 0; }
+                // -p on a tile of <= 32 sites (site lists, deep panels): the 8 consumer warps take 8 LIBRARIES of the
+                // same sites instead of 8 site ranges, so one staged chunk serves 8 rows
+                narrow = PER_LIB && ti.n <= 32;
+                if (narrow && (row % N_CONSUMER_WARPS) != 0) continue;
             }
             int32_t r0 = lo;
             bool first = true;
@@ -807,14 +835,14 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
                     ci.qbase32 = (uint32_t)qa; ci.sbase32 = (uint32_t)sa;
                     ci.flags = staged ? 1u : 0u;
                     ci.r0 = r0; ci.r1 = r1;
-                    ci.flags |= (first ? 2u : 0u) | (r1 >= hi ? 4u : 0u);
+                    ci.flags |= (first ? 2u : 0u) | (r1 >= hi ? 4u : 0u) | (narrow ? 8u : 0u);
                     sm.info[s] = ci;
                     mbar_expect_tx(&sm.full[s], bytes);
                     tma_bulk_g2s(sm.st[s].desc, P.desc + r0, db, &sm.full[s]);
                     if (qbytes) tma_bulk_g2s(sm.st[s].qual, P.qual + qa, qbytes, &sm.full[s]);
                     if (sbytes) tma_bulk_g2s(sm.st[s].seq, P.seq + sa, sbytes, &sm.full[s]);
                 } else {   // tile without reads, or the terminator
-                    ci.r0 = ci.r1 = 0; ci.flags = 2u | 4u;
+                    ci.r0 = ci.r1 = 0; ci.flags = 2u | 4u | (narrow ? 8u : 0u);
                     sm.info[s] = ci;
                     mbar_arrive(&sm.full[s]);
                 }
@@ -830,6 +858,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
 
     // =========================== CONSUMERS ===========================
     SiteState S0;
+    sm.warn[0][tid] = 0u; sm.warn[1][tid] = 0u;   // only this thread touches its two slots
     for (uint32_t item = 0;; ++item) {
         const int s = item % NSTAGE; const uint32_t ph = (item / NSTAGE) & 1u;
 #ifdef BRC_K1_PROFILE
@@ -841,12 +870,12 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
 #endif
         const ChunkInfo &ci = sm.info[s];   // stays valid until this warp arrives on empty[s]
         if (ci.work < 0) break;
-        if (ci.flags & 2u) site_reset(S0, ci, tid);   // first chunk of a tile
+        if (ci.flags & 2u) site_reset<PER_LIB>(S0, ci, tid, P.res.n_rows);   // first chunk of a tile
         if (!S0.warp_done) {
-            if (ci.flags & 1u) process_chunk<PER_LIB, true>(P, sm.st[s], sm.sacc, ci, S0, tid);
-            else process_chunk<PER_LIB, false>(P, sm.st[s], sm.sacc, ci, S0, tid);
+            if (ci.flags & 1u) process_chunk<PER_LIB, true>(P, sm.st[s], sm.sacc, sm.warn, ci, S0, tid);
+            else process_chunk<PER_LIB, false>(P, sm.st[s], sm.sacc, sm.warn, ci, S0, tid);
         }
-        if (ci.flags & 4u) site_emit(P, sm.sacc, ci, S0, tid);   // last chunk of the tile
+        if (ci.flags & 4u) site_emit<PER_LIB>(P, sm.sacc, ci, S0, tid);   // last chunk of the tile
         __syncwarp();
 #ifdef BRC_K1_PROFILE
         if (lane == 0) { atomicAdd(&g_k1prof[0], (unsigned long long)(tc1 - tc0)); atomicAdd(&g_k1prof[1], (unsigned long long)(clock64() - tc1)); }
@@ -854,7 +883,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
         if (lane == 0) mbar_arrive(&sm.empty[s]);   // this warp is done with the slot
     }
     // warning counters: warp-reduce then one atomic per warp
-    uint32_t warn_sm = S0.warn_sm, warn_nm = S0.warn_nm;
+    uint32_t warn_nm = sm.warn[0][tid], warn_sm = sm.warn[1][tid];
     for (int o = 16; o; o >>= 1) { warn_sm += __shfl_xor_sync(0xffffffffu, warn_sm, o); warn_nm += __shfl_xor_sync(0xffffffffu, warn_nm, o); }
     if (lane == 0) {
         if (warn_sm) atomicAdd(P.res.warn + 0, (unsigned long long)warn_sm);
