@@ -388,6 +388,25 @@ int main(int argc, char **argv) {
         }
     }
 
+    // Long regions are cut into consecutive windows so host staging and result buffers stay bounded (a 250 Mb chromosome
+    // at 30x would otherwise need tens of GB).  A window is just a region of the -l loop: it recomputes the site to its left
+    // (the 1-site halo), so the concatenated output equals the unsplit region's.  Only the last window of an argv region keeps
+    // argv semantics.  (With a tiny -d the max-count rule sees the window's own fetch order)
+    {
+        const int64_t W = std::getenv("BRC_CLI_WINDOW") ? std::atoll(std::getenv("BRC_CLI_WINDOW")) : 8000000;
+        std::vector<Region> cut;
+        for (const Region &g : regions) {
+            const int64_t clen = bam.lens[(size_t)g.tid];
+            const int64_t e_eff = std::min<int64_t>(g.end, std::max<int64_t>(clen, (int64_t)g.beg + 1));
+            if (e_eff - g.beg <= W) { cut.push_back(g); continue; }
+            for (int64_t b = g.beg; b < e_eff; b += W) {
+                const bool last = b + W >= e_eff;
+                cut.push_back({g.tid, (int)b, last ? g.end : (int)(b + W), last ? g.site_list : true});
+            }
+        }
+        regions.swap(cut);
+    }
+
     std::set<int> ref_loaded;
     std::string chrom;
     Rec rec;
@@ -461,9 +480,9 @@ int main(int argc, char **argv) {
         brc_end_region(eng);
         t_decode += now() - d1;
         // site-list regions are independent: flush in batches; argv regions share the deletion queue -> one batch
-        if (g.site_list && (pushed > 4000000 || gi + 1 == regions.size())) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
+        const bool next_is_argv_chain = gi + 1 < regions.size() && !g.site_list;     // argv regions share the deletion queue: keep them in one batch
+        if (gi + 1 == regions.size() || (!next_is_argv_chain && pushed > 1500000)) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
     }
-    if (!regions.empty() && !regions.back().site_list) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } }
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
     brc_destroy(eng);
     return 0;

@@ -90,3 +90,28 @@ def test_cli_synthetic_bam_matches_oracle(tmp_path):
         p = subprocess.run([exe, "-w", "0", "-f", os.path.join(d, "ref.fa")] + argv + [os.path.join(d, "s.bam"), "chr1:1001-38000"], capture_output=True)
         assert p.returncode == 0, p.stderr.decode()[-2000:]
         assert p.stdout.decode("latin-1") == want
+
+
+@pytest.mark.gpu
+def test_cli_windowed_long_region_equals_unsplit(tmp_path):
+    """brc-readcount cuts long regions into windows (bounded memory); the concatenation must equal the unsplit output,
+    deletions across window edges included."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import synth
+    exe = _cli()
+    case = cases.synthetic_case(L=30000, depth=30, seed=41, regions=((0, 1, 30000),), site_list=False)
+    name, L, seq, _ = case["contigs"][0]
+    d = str(tmp_path)
+    synth.write_fasta(os.path.join(d, "ref.fa"), name, np.frombuffer(seq, dtype=np.uint8))
+    synth.write_sam(os.path.join(d, "s.sam"), case["batch"], [(name, L)])
+    subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-o", os.path.join(d, "s.bam"), os.path.join(d, "s.sam")])
+    subprocess.check_call([REF_SAMTOOLS, "index", os.path.join(d, "s.bam")])
+    outs = []
+    for win in ("100000000", "3777"):
+        p = subprocess.run([exe, "-w", "0", "-p", "-f", os.path.join(d, "ref.fa"), os.path.join(d, "s.bam"), "chr1:1-30000"],
+                           capture_output=True, env=dict(os.environ, BRC_CLI_WINDOW=win))
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+        outs.append(p.stdout)
+    assert outs[0] == outs[1] and outs[0].count(b"\n") > 29000
