@@ -479,15 +479,17 @@ struct Terms { float q2term, d3pterm; double posterm; };
 __device__ __forceinline__ Terms event_terms(bool fast, int qpos, int q2pos, int tpi, int lclip, int clen, float fl, float fclen,
                                              float rcp_l, float rcp_c) {
     Terms t;
-    const float a_q2 = (float)abs(qpos - q2pos), a_3p = (float)abs(qpos - tpi);
+    const float a_3p = (float)abs(qpos - tpi);
     if (fast) {
-        t.q2term = div_small(a_q2, fl, rcp_l);
         t.d3pterm = div_small(a_3p, fl, rcp_l);
+        // the Q2 term is only accumulated when the read has a Q2 position, and for most forward reads that position IS
+        // the effective 3' end (R:...:229-238): both tests are uniform across the warp (one read per iteration)
+        t.q2term = (q2pos < 0 || q2pos == tpi) ? t.d3pterm : div_small((float)abs(qpos - q2pos), fl, rcp_l);
         // |(qpos-lclip) - clen/2| / (clen/2)  ==  |2(qpos-lclip) - clen| / clen   (numerator and denominator exact)
         const float f = div_small((float)abs(2 * (qpos - lclip) - clen), fclen, rcp_c);
         t.posterm = __dsub_rn(1.0, f32_to_f64_nonneg(f));
     } else {
-        t.q2term = __fdiv_rn(a_q2, fl);
+        t.q2term = __fdiv_rn((float)abs(qpos - q2pos), fl);
         t.d3pterm = __fdiv_rn(a_3p, fl);
         const float rc = __fmul_rn(fclen, 0.5f);
         const float f = __fdiv_rn(fabsf(__fsub_rn((float)(qpos - lclip), rc)), rc);

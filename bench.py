@@ -380,13 +380,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--contig-len", type=int, default=CONTIG_LEN)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-sample-bp", type=int, default=150_000)
+    ap.add_argument("--ref-sample-bp", type=int, default=0, help="bases of the synthetic workload each reference process handles per step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
+        if args.ref_sample_bp <= 0:   # keep the whole --steps K run within a few minutes (≈6 k positions/s per process when all cores are busy)
+            args.ref_sample_bp = max(5_000, min(150_000, 720_000 // max(args.steps, 1)))
         return reference_arm(args)
+    if args.ref_sample_bp <= 0:
+        args.ref_sample_bp = 150_000
     return our_arm(args)
 
 

@@ -115,3 +115,62 @@ def test_pipelined_push_path_many_chunks(monkeypatch):
         etext, edump, _, _ = cases.run_engine(case, flags, site_list=True)
         assert etext == otext
         assert edump == odump
+
+
+def _long_read_case(seed=77, L=120000):
+    """Reads of 3-25 kb (beyond the reciprocal-division fast path at 2048 bp and beyond a K0/K1 shared-memory stage)."""
+    import numpy as np
+    from bam_readcount_b200 import synth
+    from bam_readcount_b200.batch import BatchBuilder
+    import edge_cases
+    rng = np.random.default_rng(seed)
+    ref = synth.synth_reference(L, seed)
+    recs = []
+    for i in range(60):
+        lq = int(rng.choice([3000, 5000, 9000, 16000, 25000, 150]))
+        p = int(rng.integers(10, L - 2 * lq - 100))
+        ops, span = edge_cases._rand_cigar(rng, lq)
+        seq = edge_cases._read_from_ref(rng, ref, p, ops, sub_rate=0.01)
+        flag = 16 if rng.random() < 0.5 else 0
+        recs.append(dict(tid=0, pos=p, flag=flag, mapq=int(rng.choice([60, 30, 0])), lib=int(rng.integers(0, 3)),
+                         cigar="".join(f"{l}{o}" for l, o in ops), seq=seq, qual=edge_cases._quals(rng, lq, bool(flag)),
+                         nm=int(rng.integers(0, 50)), sm=None, qname=f"L{i}"))
+    recs.sort(key=lambda r: r["pos"])
+    bb = BatchBuilder()
+    for r in recs:
+        bb.add_sam(**r)
+    return dict(name="longreads", contigs=[("c", L, ref.tobytes(), 0)], batch=bb.build(), regions=[(0, 1, L)], site_list=True,
+                lib_names=["lib0", "lib1", "lib2"])
+
+
+def test_long_reads_exact_slow_paths():
+    case = _long_read_case()
+    for flags in (dict(), dict(per_lib=True, min_mapq=20, min_bq=20)):
+        otext, odump, owarn = cases.run_oracle(case, flags, site_list=True)
+        etext, edump, ewarn, _ = cases.run_engine(case, flags, site_list=True)
+        assert etext == otext, _first_diff(etext, otext)
+        assert edump == odump, _first_diff(edump, odump)
+
+
+def test_two_contigs_and_empty_region_in_one_batch():
+    """Several regions on two contigs (two reference windows, region_of_read path) plus a region without reads."""
+    import numpy as np
+    from bam_readcount_b200 import synth
+    from bam_readcount_b200.batch import ReadBatch
+    a = cases.synthetic_case(L=8000, depth=25, seed=51)
+    b = cases.synthetic_case(L=9000, depth=35, seed=52)
+    bb = b["batch"]
+    bb = ReadBatch(**{**{k: getattr(bb, k) for k in ("pos", "flag", "mapq", "lib", "l_qseq", "nm", "sm", "cigar_off", "cigar", "seq_off",
+                                                         "seq", "qual_off", "qual")}, "tid": np.full(bb.n_reads, 1, np.int32)})
+    batch = ReadBatch.concat([a["batch"], bb])
+    gap = synth.synth_reference(500, 3).tobytes()
+    case = dict(name="twocontigs", contigs=[a["contigs"][0], ("chr2", 9000, b["contigs"][0][2], 0)], batch=batch,
+                regions=[(0, 100, 3000), (0, 7990, 8000), (1, 1, 50), (1, 4000, 8999), (0, 3500, 3600)], site_list=True,
+                lib_names=a["lib_names"])
+    # make the tail of contig 1 read-free: region (0, 7990, 8000) has no reads (synth reads stop at L-153)
+    for flags in (dict(insertion_centric=True), dict(per_lib=True)):
+        otext, odump, _ = cases.run_oracle(case, flags, site_list=True)
+        etext, edump, _, _ = cases.run_engine(case, flags, site_list=True)
+        assert etext == otext, _first_diff(etext, otext)
+        assert edump == odump, _first_diff(edump, odump)
+    _ = gap
