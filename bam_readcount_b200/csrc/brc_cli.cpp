@@ -74,7 +74,8 @@ struct Bgzf {
         return true;
     }
     bool seek(uint64_t voff) {
-        if (!load_block(voff >> 16)) return false;
+        // sorted site lists keep landing in the block that is already inflated
+        if (!((voff >> 16) == block_coff && !block.empty() && !eof) && !load_block(voff >> 16)) return false;
         upos = (size_t)(voff & 0xFFFF);
         return true;
     }

@@ -72,7 +72,7 @@ void brc_destroy(brc_engine *e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (auto &r : e->refs) r.dev.release();
-    DevBuf *bufs[] = {&e->d_refs, &e->d_desc, &e->d_tiles, &e->d_tile_lo, &e->d_tile_hi, &e->d_regions, &e->d_region_of_read,
+    DevBuf *bufs[] = {&e->d_refs, &e->d_desc, &e->d_tiles, &e->d_tile_lo, &e->d_tile_hi, &e->d_regions,
                       &e->d_ncover, &e->d_npass, &e->d_flags, &e->d_pbase, &e->d_sec_head, &e->d_pstats, &e->d_sec_count,
                       &e->d_sec_next, &e->d_sec_kind, &e->d_sec_len, &e->d_sec_read, &e->d_sec_qpos, &e->d_sec_stats, &e->d_warn};
     for (auto *b : bufs) b->release();

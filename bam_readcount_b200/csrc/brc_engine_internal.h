@@ -106,7 +106,7 @@ struct brc_engine {
 
     // device buffers
     brc::DevBuf d_in[14];            // uploaded read arrays (push path)
-    brc::DevBuf d_desc, d_tiles, d_tile_lo, d_tile_hi, d_regions, d_region_of_read;
+    brc::DevBuf d_desc, d_tiles, d_tile_lo, d_tile_hi, d_regions;
     brc::DevBuf d_ncover, d_npass, d_flags, d_pbase, d_sec_head, d_pstats;
     brc::DevBuf d_sec_count, d_sec_next, d_sec_kind, d_sec_len, d_sec_read, d_sec_qpos, d_sec_stats, d_warn;
     brc::ReadsDev dev_reads{};       // what the kernels read (push path: d_in; device path: caller's pointers)
@@ -123,7 +123,6 @@ struct brc_engine {
     std::string fmt_cache; int64_t fmt_key[3] = {-2, -2, -2}; bool fmt_valid = false;
 
     int launch_count = 0;
-    float stage_ms[3] = {0, 0, 0};
 };
 
 namespace brc {
