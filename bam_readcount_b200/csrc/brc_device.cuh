@@ -60,9 +60,12 @@ struct __align__(16) ReadDesc {
 static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
 
 // K1 shared-memory staging: capacity of ONE slot of the 2-stage TMA ring
-constexpr int STAGE_READS = 96;                 // descriptors per chunk
-constexpr int STAGE_QUAL = 96 * 152 + 32;          // staged quality bytes per chunk (incl. 16-B alignment slack both ends)
-constexpr int STAGE_SEQ = 96 * 76 + 32;            // staged packed-base bytes per chunk
+#ifndef BRC_STAGE_READS
+#define BRC_STAGE_READS 96
+#endif
+constexpr int STAGE_READS = BRC_STAGE_READS;                 // descriptors per chunk
+constexpr int STAGE_QUAL = STAGE_READS * 152 + 32;          // staged quality bytes per chunk (incl. 16-B alignment slack both ends)
+constexpr int STAGE_SEQ = STAGE_READS * 76 + 32;            // staged packed-base bytes per chunk
 
 struct TileInfo {
     int32_t pos0;       // absolute position of the tile's first site
