@@ -6,9 +6,11 @@
 // host, in file order), end_region ≙ bam_plbuf_push(0).  All arithmetic of the hot path runs
 // in the CUDA kernels of brc_kernels.cu; this file only batches, copies and launches.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <chrono>
 
 #include "brc_engine_internal.h"
 
@@ -225,6 +227,7 @@ int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_
 
 // Parallel scan of a batch: are all reads admitted by the pileup buffer as they are (so the batch can be used in
 // place), and what is the largest bam_endpos?  The -d rule cannot fire when the whole batch is smaller than max_cnt.
+static double wall_ms_fwd() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct BatchScan { bool ok = true; int64_t max_end = 0; int64_t indel_ops = 0; };
 static BatchScan scan_batch(const brc_read_batch *b, int32_t rtid, int per_lib, int n_rows) {
     const int64_t n = b->n_reads;
@@ -262,6 +265,7 @@ static BatchScan scan_batch(const brc_read_batch *b, int32_t rtid, int per_lib, 
 
 int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
     if (!e || !b) return BRC_E_INVALID;
+    const double tp0 = wall_ms_fwd();
     if (!e->region_open) return set_error(e, BRC_E_INVALID, "push_reads: no open region");
     if (e->is_borrowed) materialize_borrowed(e);
     brc_region &rg = e->regions.back();
@@ -272,6 +276,7 @@ int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
     if (e->regions.size() == 1 && e->reads.n() == 0 && b->n_reads > 0 && b->n_reads < (int64_t)e->cfg.max_cnt &&
         b->n_reads < 0x7fffffffLL && e->adm.max_pos < 0) {
         const BatchScan sc = scan_batch(b, rtid, e->cfg.per_lib, e->n_rows);
+        if (std::getenv("BRC_PIPE_TIMING")) std::fprintf(stderr, "[brc pipe] scan_batch %.2f ms\n", wall_ms_fwd() - tp0);
         if (sc.ok) {
             e->is_borrowed = true; e->borrowed = *b;
             e->n_indel_ops += sc.indel_ops;
@@ -469,7 +474,11 @@ static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetch
 // chunk c+1, the kernels of chunk c and the D2H copy of the finished tiles of chunk c-1 overlap (PCIe is full
 // duplex; three streams + events).  Reads are position-sorted, so every tile that ends at or before the first
 // position of chunk c+1 is complete once chunk c is on the device.
+static double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int compute_pipelined(brc_engine *e) {
+    const bool timing = std::getenv("BRC_PIPE_TIMING") != nullptr;
+    const double t0 = wall_ms();
     const brc_read_batch &B = e->borrowed;
     const int64_t n = B.n_reads;
     const brc_region &rg = e->regions[0];
@@ -547,10 +556,16 @@ static int compute_pipelined(brc_engine *e) {
             tile_done = tile_to;
         }
     }
+    const double t1 = wall_ms();
     CU(cudaEventRecord(e->ev[1], sk), "event");
     CU(cudaEventRecord(e->ev[2], sk), "event");
+    CU(cudaStreamSynchronize(e->s_in), "sync H2D");
+    const double t2 = wall_ms();
     CU(cudaStreamSynchronize(sk), "sync kernels");
+    const double t3 = wall_ms();
     CU(cudaStreamSynchronize(e->s_out), "sync D2H");
+    const double t4 = wall_ms();
+    if (timing) std::fprintf(stderr, "[brc pipe] chunks %d  enqueue %.2f ms  H2D done +%.2f  kernels done +%.2f  D2H done +%.2f (ms since compute start)\n", n_chunks, t1 - t0, t2 - t0, t3 - t0, t4 - t0);
     int32_t cnt = 0;
     CU(cudaMemcpy(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost), "D2H sec_count");
     e->h_n_sec = cnt;
