@@ -80,6 +80,14 @@ def main():
     decode_fixture("test.bam", "test_bam.npz")
     decode_fixture("test_bad_rg.bam", "test_bam_bad_rg.npz")
 
+    # config 2b: the CRAM fixture through the reference binary (the reference ships no expected file for it)
+    for flags, name in ((["-p"], "ref_cram_twolib_perlib.txt"), ([], "ref_cram_twolib_alllib.txt")):
+        out, err, rc = run_reference_binary(flags + ["-l", "twolib_site_list.txt", "-f", "rand1k.fa", "twolib.sorted.cram"], cwd=TD)
+        assert rc == 0
+        with gzip.open(os.path.join(HERE, name + ".gz"), "wb", compresslevel=9) as fh:
+            fh.write(out.encode("latin-1"))
+        print(name, len(out.splitlines()), "lines")
+
     jobs = []
     syn = cases.synthetic_case(L=12000, depth=30, seed=11, regions=((0, 1000, 4000),), site_list=False)
     for fname, fl in cases.FLAG_SETS.items():

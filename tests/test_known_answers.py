@@ -69,3 +69,35 @@ def test_engine_known_answers(k):
 def test_engine_max_count_table(d):
     text, _, _, _ = cases.run_engine(_d_case(), dict(max_cnt=d), want_dump=False)
     assert [int(l.split("\t")[3]) for l in text.strip().split("\n")] == D_TABLE[d]
+
+
+# ---- BASELINE config 2b: test-data/twolib.sorted.cram (-p, -l twolib_site_list.txt, -f rand1k.fa) -------------------------
+# CRAM decode is host I/O outside the hot path; the fixture's four records (samtools view: 60M, MAPQ 60, no qualities -> 0xFF,
+# NM:i:0, RG reads{1,2}_id -> LB reads{1,2}_lb, starts 1/61/121/181) are rebuilt here and the output is compared with what the
+# reference binary prints for the CRAM itself (tests/golden/ref_cram_twolib_*.txt.gz, made by make_golden.py).
+def _cram_case():
+    import os
+    from bam_readcount_b200.bamio import Fasta
+    fa = Fasta(os.path.join(cases.GOLDEN, "rand1k.fa"))
+    ref = fa.fetch("rand1k")
+    bb = BatchBuilder()
+    for i, (start, lib) in enumerate(((0, 0), (60, 0), (120, 1), (180, 1))):
+        bb.add_sam(tid=0, pos=start, flag=0, mapq=60, lib=lib, cigar="60M", seq=ref[start:start + 60].decode(),
+                   qual=np.full(60, 255, np.uint8), nm=0, sm=None, qname=f"read{lib + 1}-{i % 2 + 1}")
+    return dict(name="cram", contigs=[("rand1k", 1000, ref, 0)], batch=bb.build(), regions=[(0, 50, 60)], site_list=True,
+                lib_names=["reads1_lb", "reads2_lb"])
+
+
+@pytest.mark.parametrize("per_lib", [True, False])
+def test_oracle_cram_fixture_records(per_lib):
+    text, _, _ = cases.run_oracle(_cram_case(), dict(per_lib=per_lib))
+    want = cases.load_golden_text("ref_cram_twolib_perlib.txt" if per_lib else "ref_cram_twolib_alllib.txt")
+    assert text == want and len(want.splitlines()) == 11
+    assert "A:1:60.00:255.00:60.00:1:0:0.37:0.00:0.00:1:0.15:60.00:0.15" in want.splitlines()[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_lib", [True, False])
+def test_engine_cram_fixture_records(per_lib):
+    text, _, _, _ = cases.run_engine(_cram_case(), dict(per_lib=per_lib), want_dump=False)
+    assert text == cases.load_golden_text("ref_cram_twolib_perlib.txt" if per_lib else "ref_cram_twolib_alllib.txt")
