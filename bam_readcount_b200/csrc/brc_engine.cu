@@ -121,6 +121,7 @@ int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64
 
 int brc_reset(brc_engine *e) {
     if (!e) return BRC_E_INVALID;
+    if (e->h2d_chunks) { cudaSetDevice(e->cfg.device); cudaStreamSynchronize(e->s_in); e->h2d_chunks = 0; }
     e->reads.clear(); e->is_borrowed = false; e->regions.clear(); e->region_open = false; e->adm.reset(); e->n_indel_ops = 0;
     e->results_valid = false; e->planned = false; e->tiles.clear(); e->regions_dev.clear(); e->n_slots = 0;
     for (auto &w : e->warn_counts) w = 0;
@@ -129,6 +130,7 @@ int brc_reset(brc_engine *e) {
 
 // A borrowed batch becomes an owned copy (bulk memcpy) as soon as anything else is pushed after it.
 static void materialize_borrowed(brc_engine *e) {
+    if (e->h2d_chunks) { cudaStreamSynchronize(e->s_in); e->h2d_chunks = 0; }
     const brc_read_batch &B = e->borrowed;
     HostReads &H = e->reads;
     const size_t n = (size_t)B.n_reads;
@@ -225,6 +227,8 @@ int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag, uint8_
     return BRC_OK;
 }
 
+static int issue_h2d_chunks(brc_engine *e);
+
 // Parallel scan of a batch: are all reads admitted by the pileup buffer as they are (so the batch can be used in
 // place), and what is the largest bam_endpos?  The -d rule cannot fire when the whole batch is smaller than max_cnt.
 static double wall_ms_fwd() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -275,6 +279,12 @@ int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
     // keep a VIEW of the caller's arrays — brc_compute DMAs straight out of them (pin them for full PCIe speed).
     if (e->regions.size() == 1 && e->reads.n() == 0 && b->n_reads > 0 && b->n_reads < (int64_t)e->cfg.max_cnt &&
         b->n_reads < 0x7fffffffLL && e->adm.max_pos < 0) {
+        // Optional (BRC_EARLY_H2D=1): start the copies before the admission scan.  Measured on B200/PCIe Gen5 it is SLOWER end to end
+        // (28.9 vs 23.2 ms): the uploads run ahead alone and the result download then has the link to itself at the end, instead of
+        // both directions streaming concurrently for the whole step — so the default issues H2D from brc_compute.
+        e->borrowed = *b; e->h2d_chunks = 0;
+        cudaSetDevice(e->cfg.device);
+        const bool early = std::getenv("BRC_EARLY_H2D") && issue_h2d_chunks(e) == BRC_OK;
         const BatchScan sc = scan_batch(b, rtid, e->cfg.per_lib, e->n_rows);
         if (std::getenv("BRC_PIPE_TIMING")) std::fprintf(stderr, "[brc pipe] scan_batch %.2f ms\n", wall_ms_fwd() - tp0);
         if (sc.ok) {
@@ -284,6 +294,8 @@ int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
             rg.read_hi = b->n_reads;
             return BRC_OK;
         }
+        if (early) { cudaStreamSynchronize(e->s_in); }   // not usable as is: drop the speculative upload, take the copying path
+        e->h2d_chunks = 0;
     }
     for (int64_t i = 0; i < b->n_reads; ++i) {
         const uint64_t c0 = b->cigar_off[i], c1 = b->cigar_off[i + 1];
@@ -476,6 +488,39 @@ static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetch
 // position of chunk c+1 is complete once chunk c is on the device.
 static double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Device buffers + chunked H2D of a borrowed batch on s_in; records pipe_ev[2c] after chunk c.  Called speculatively from
+// brc_push_reads (so the copies overlap the admission scan and the caller's remaining host work) or from brc_compute.
+static int issue_h2d_chunks(brc_engine *e) {
+    const brc_read_batch &B = e->borrowed;
+    const int64_t n = B.n_reads;
+    if (!e->s_in) CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking), "stream");
+    if (!e->s_out) CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking), "stream");
+    const uint64_t n_cig = B.cigar_off[n], n_seq = B.seq_off[n], n_qual = B.qual_off[n];
+    const size_t tot[13] = {(size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 2, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
+                            (size_t)(n + 1) * 8, (size_t)n_cig * 4, (size_t)(n + 1) * 8, (size_t)n_seq, (size_t)(n + 1) * 8, (size_t)n_qual};
+    for (int k = 0; k < 13; ++k) CU(e->d_in[k].reserve(tot[k] + 16), "cudaMalloc(reads)");
+    size_t in_bytes = 0; for (int k = 0; k < 13; ++k) in_bytes += tot[k];
+    int n_chunks = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(in_bytes >> 26)));   // ~64 MiB of input per chunk
+    n_chunks = (int)std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 4096));
+    if (const char *ov = std::getenv("BRC_PIPE_CHUNKS")) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::atoi(ov), std::max<int64_t>(1, n)));   // test hook
+    while (e->pipe_ev.size() < (size_t)(2 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
+    if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, e->s_in), "memset lib");
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
+        #define H2D(k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, e->s_in), "H2D chunk")
+        H2D(0, B.pos, a, b - a, 4); H2D(1, B.flag, a, b - a, 2); H2D(2, B.mapq, a, b - a, 1);
+        if (B.lib) H2D(3, B.lib, a, b - a, 2);
+        H2D(4, B.l_qseq, a, b - a, 4); H2D(5, B.nm, a, b - a, 4); H2D(6, B.sm, a, b - a, 4);
+        H2D(7, B.cigar_off, a, b - a + 1, 8); H2D(8, B.cigar, B.cigar_off[a], B.cigar_off[b] - B.cigar_off[a], 4);
+        H2D(9, B.seq_off, a, b - a + 1, 8); H2D(10, B.seq, B.seq_off[a], B.seq_off[b] - B.seq_off[a], 1);
+        H2D(11, B.qual_off, a, b - a + 1, 8); H2D(12, B.qual, B.qual_off[a], B.qual_off[b] - B.qual_off[a], 1);
+        #undef H2D
+        CU(cudaEventRecord(e->pipe_ev[2 * c], e->s_in), "event");
+    }
+    e->h2d_chunks = n_chunks;
+    return BRC_OK;
+}
+
 static int compute_pipelined(brc_engine *e) {
     const bool timing = std::getenv("BRC_PIPE_TIMING") != nullptr;
     const double t0 = wall_ms();
@@ -484,12 +529,8 @@ static int compute_pipelined(brc_engine *e) {
     const brc_region &rg = e->regions[0];
     const int64_t n_tiles = (int64_t)e->tiles.size();
     const int64_t rs = (int64_t)e->n_rows * e->n_slots;
-    if (!e->s_in) CU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking), "stream");
-    if (!e->s_out) CU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking), "stream");
-    const uint64_t n_cig = B.cigar_off[n], n_seq = B.seq_off[n], n_qual = B.qual_off[n];
-    const size_t tot[13] = {(size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 2, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
-                            (size_t)(n + 1) * 8, (size_t)n_cig * 4, (size_t)(n + 1) * 8, (size_t)n_seq, (size_t)(n + 1) * 8, (size_t)n_qual};
-    for (int k = 0; k < 13; ++k) CU(e->d_in[k].reserve(tot[k] + 16), "cudaMalloc(reads)");
+    if (e->h2d_chunks == 0) { int rc0 = issue_h2d_chunks(e); if (rc0 != BRC_OK) return rc0; }
+    const int n_chunks = e->h2d_chunks;
     ReadsDev &R = e->dev_reads;
     R.n_reads = n; R.pos = e->d_in[0].as<int32_t>(); R.flag = e->d_in[1].as<uint16_t>(); R.mapq = e->d_in[2].as<uint8_t>();
     R.lib = e->d_in[3].as<uint16_t>(); R.l_qseq = e->d_in[4].as<int32_t>(); R.nm = e->d_in[5].as<int32_t>(); R.sm = e->d_in[6].as<int32_t>();
@@ -500,32 +541,15 @@ static int compute_pipelined(brc_engine *e) {
     CU(e->h_ncover.reserve(rs1 * 4), "pin"); CU(e->h_npass.reserve(rs1 * 4), "pin"); CU(e->h_flags.reserve(rs1), "pin");
     CU(e->h_pbase.reserve(rs1), "pin"); CU(e->h_sec_head.reserve(rs1 * 4), "pin"); CU(e->h_pstats.reserve(rs1 * 4 * N_STATS), "pin");
 
-    const size_t in_bytes = tot[0] + tot[1] + tot[2] + tot[3] + tot[4] + tot[5] + tot[6] + tot[7] + tot[8] + tot[9] + tot[10] + tot[11] + tot[12];
-    int n_chunks = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(in_bytes >> 26)));   // ~64 MiB of input per chunk
-    n_chunks = (int)std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 4096));
-    if (const char *ov = std::getenv("BRC_PIPE_CHUNKS")) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::atoi(ov), std::max<int64_t>(1, n)));   // test hook
-    while (e->pipe_ev.size() < (size_t)(2 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
-
     PrecomputeParams P0; PileupParams P1;
     make_params(e, nullptr, P0, P1);
     cudaStream_t sk = e->stream;
     e->launch_count = 0;
     CU(cudaEventRecord(e->ev[0], sk), "event");
     CU(launch_init_tiles(P0.tile_lo, P0.tile_hi, n_tiles, P1.res.sec_count, P1.res.warn, sk), "launch init_tiles"); e->launch_count++;
-    if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, e->s_in), "memset lib");
     int64_t tile_done = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
-        // ---- H2D of reads [a, b) (offsets [a, b]) ----
-        #define H2D(k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, e->s_in), "H2D chunk")
-        H2D(0, B.pos, a, b - a, 4); H2D(1, B.flag, a, b - a, 2); H2D(2, B.mapq, a, b - a, 1);
-        if (B.lib) H2D(3, B.lib, a, b - a, 2);
-        H2D(4, B.l_qseq, a, b - a, 4); H2D(5, B.nm, a, b - a, 4); H2D(6, B.sm, a, b - a, 4);
-        H2D(7, B.cigar_off, a, b - a + 1, 8); H2D(8, B.cigar, B.cigar_off[a], B.cigar_off[b] - B.cigar_off[a], 4);
-        H2D(9, B.seq_off, a, b - a + 1, 8); H2D(10, B.seq, B.seq_off[a], B.seq_off[b] - B.seq_off[a], 1);
-        H2D(11, B.qual_off, a, b - a + 1, 8); H2D(12, B.qual, B.qual_off[a], B.qual_off[b] - B.qual_off[a], 1);
-        #undef H2D
-        CU(cudaEventRecord(e->pipe_ev[2 * c], e->s_in), "event");
         // ---- kernels: K0 on the chunk, K1 on the tiles it completes ----
         CU(cudaStreamWaitEvent(sk, e->pipe_ev[2 * c], 0), "wait");
         P0.read_begin = a; P0.read_end = b;
@@ -569,6 +593,7 @@ static int compute_pipelined(brc_engine *e) {
     int32_t cnt = 0;
     CU(cudaMemcpy(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost), "D2H sec_count");
     e->h_n_sec = cnt;
+    e->h2d_chunks = 0;
     if ((int64_t)cnt > e->sec_cap) return BRC_E_OVERFLOW;
     return fetch_results(e, sk, true);
 }
@@ -610,6 +635,7 @@ int brc_compute(brc_engine *e) {
         if (rc != BRC_E_OVERFLOW) return rc;
         // pool too small: everything is on the device already; fall through to the plain path with a larger pool
     }
+    if (e->h2d_chunks) { cudaStreamSynchronize(e->s_in); e->h2d_chunks = 0; }   // a speculative upload is not used on this path
     // H2D of the read arrays (borrowed batches: straight from the caller's buffers)
     std::vector<uint16_t> zero_lib;
     const uint16_t *h_lib = bw ? B.lib : H.lib.data();

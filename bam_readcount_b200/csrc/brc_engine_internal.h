@@ -77,6 +77,7 @@ struct brc_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined push path
     std::vector<cudaEvent_t> pipe_ev;
+    int h2d_chunks = 0;              // >0: the borrowed batch's H2D copies are already in flight on s_in (issued by brc_push_reads)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
