@@ -21,6 +21,8 @@
 #include <vector>
 #include <zlib.h>
 #include <chrono>
+#include <thread>
+#include <unistd.h>
 
 #include "../../include/brc_engine.h"
 
@@ -31,46 +33,96 @@ namespace {
 // ------------------------------------------------------------------------------------------
 struct Bgzf {
     FILE *fp = nullptr;
-    std::vector<uint8_t> block, raw;
+    std::vector<uint8_t> block;
     uint64_t block_coff = 0;     // compressed offset of the current block
     uint64_t next_coff = 0;      // compressed offset of the next block
     size_t upos = 0;             // position inside `block`
     bool eof = false;
+    // read-ahead: a span of consecutive blocks is read with one fread and inflated by several threads
+    struct Ahead { uint64_t coff, next; std::vector<uint8_t> data; bool ok; };
+    std::vector<Ahead> ahead; size_t ahead_pos = 0;
+    std::vector<uint8_t> raw;
+    int n_threads = 8;
+    size_t span_blocks = 64;
 
-    bool open(const std::string &path) { fp = std::fopen(path.c_str(), "rb"); return fp != nullptr; }
+    bool open(const std::string &path) {
+        fp = std::fopen(path.c_str(), "rb");
+        unsigned hw = std::thread::hardware_concurrency();
+        n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+        return fp != nullptr;
+    }
     ~Bgzf() { if (fp) std::fclose(fp); }
 
-    bool load_block(uint64_t coff) {
-        if (fseeko(fp, (off_t)coff, SEEK_SET) != 0) return false;
-        uint8_t h[18];
-        if (std::fread(h, 1, 18, fp) != 18) { eof = true; block.clear(); upos = 0; return false; }
-        if (h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return false;
-        const uint16_t xlen = (uint16_t)(h[10] | (h[11] << 8));
-        // BC subfield is first in every BGZF writer; scan anyway
-        std::vector<uint8_t> extra(xlen);
-        std::memcpy(extra.data(), h + 12, std::min<size_t>(6, xlen));
-        if (xlen > 6 && std::fread(extra.data() + 6, 1, xlen - 6, fp) != (size_t)(xlen - 6)) return false;
+    static bool inflate_block(const uint8_t *src, size_t clen, std::vector<uint8_t> &dst, uint32_t isize) {
+        dst.resize(isize);
+        if (!isize) return true;
+        z_stream zs{};
+        if (inflateInit2(&zs, -15) != Z_OK) return false;
+        zs.next_in = const_cast<uint8_t *>(src); zs.avail_in = (uInt)clen; zs.next_out = dst.data(); zs.avail_out = isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        return rc == Z_STREAM_END;
+    }
+    // parse one block header at raw[o..]; returns total block size (0 on error / truncated)
+    static size_t block_size(const uint8_t *h, size_t avail, size_t &hdr_len) {
+        if (avail < 18 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) return 0;
+        const size_t xlen = (size_t)(h[10] | (h[11] << 8));
+        if (avail < 12 + xlen) return 0;
         int bsize = -1;
         for (size_t i = 0; i + 4 <= xlen;) {
-            const uint16_t sl = (uint16_t)(extra[i + 2] | (extra[i + 3] << 8));
-            if (extra[i] == 'B' && extra[i + 1] == 'C' && sl == 2) bsize = extra[i + 4] | (extra[i + 5] << 8);
+            const size_t sl = (size_t)(h[12 + i + 2] | (h[12 + i + 3] << 8));
+            if (h[12 + i] == 'B' && h[12 + i + 1] == 'C' && sl == 2) bsize = h[12 + i + 4] | (h[12 + i + 5] << 8);
             i += 4 + sl;
         }
-        if (bsize < 0) return false;
-        const size_t clen = (size_t)bsize + 1 - 12 - xlen - 8;
-        raw.resize(clen + 8);
-        if (std::fread(raw.data(), 1, clen + 8, fp) != clen + 8) return false;
-        const uint32_t isize = raw[clen + 4] | (raw[clen + 5] << 8) | (raw[clen + 6] << 16) | ((uint32_t)raw[clen + 7] << 24);
-        block.resize(isize);
-        if (isize) {
-            z_stream zs{};
-            if (inflateInit2(&zs, -15) != Z_OK) return false;
-            zs.next_in = raw.data(); zs.avail_in = (uInt)clen; zs.next_out = block.data(); zs.avail_out = isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) return false;
+        if (bsize < 0) return 0;
+        hdr_len = 12 + xlen;
+        return (size_t)bsize + 1;
+    }
+    bool fill_ahead(uint64_t coff) {
+        ahead.clear(); ahead_pos = 0;
+        if (fseeko(fp, (off_t)coff, SEEK_SET) != 0) return false;
+        raw.resize(span_blocks * 65536 + 65536);
+        const size_t got = std::fread(raw.data(), 1, raw.size(), fp);
+        if (got < 18) { eof = true; return false; }
+        struct Job { size_t off, hdr, total; };
+        std::vector<Job> jobs;
+        for (size_t o = 0; o < got && jobs.size() < span_blocks;) {
+            size_t hdr = 0; const size_t tot = block_size(raw.data() + o, got - o, hdr);
+            if (!tot || o + tot > got) break;
+            jobs.push_back({o, hdr, tot}); o += tot;
         }
-        block_coff = coff; next_coff = coff + (uint64_t)bsize + 1; upos = 0; eof = false;
+        if (jobs.empty()) return false;
+        ahead.resize(jobs.size());
+        auto work = [&](size_t t) {
+            for (size_t j = t; j < jobs.size(); j += (size_t)n_threads) {
+                const Job &jb = jobs[j];
+                const uint8_t *b = raw.data() + jb.off;
+                const size_t clen = jb.total - jb.hdr - 8;
+                const uint8_t *tail = b + jb.total - 4;
+                const uint32_t isize = tail[0] | (tail[1] << 8) | (tail[2] << 16) | ((uint32_t)tail[3] << 24);
+                ahead[j].coff = coff + jb.off; ahead[j].next = coff + jb.off + jb.total;
+                ahead[j].ok = inflate_block(b + jb.hdr, clen, ahead[j].data, isize);
+            }
+        };
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)n_threads, jobs.size());
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, (size_t)t);
+        work(0);
+        for (auto &x : th) x.join();
+        return true;
+    }
+    bool load_block(uint64_t coff) {
+        if (!(ahead_pos < ahead.size() && ahead[ahead_pos].coff == coff)) {
+            // look inside the current span first (seeks within it), else read a new span
+            bool found = false;
+            for (size_t j = 0; j < ahead.size(); ++j) if (ahead[j].coff == coff && !ahead[j].data.empty()) { ahead_pos = j; found = true; break; }
+            if (!found && !fill_ahead(coff)) { block.clear(); upos = 0; return false; }
+        }
+        Ahead &a = ahead[ahead_pos];
+        if (!a.ok) return false;
+        block = a.data;                 // keep the span entry intact: sorted site lists revisit blocks
+        block_coff = a.coff; next_coff = a.next; upos = 0; eof = false;
+        ++ahead_pos;
         return true;
     }
     bool seek(uint64_t voff) {
@@ -328,7 +380,15 @@ int main(int argc, char **argv) {
     if (dist_arg == "1" || dist_arg == "true") { std::fprintf(stderr, "Not currently supporting distributions\n"); return 1; }
     (void)max_warn;
 
+    // CUDA context creation takes a second or two: do it while the BAM header, index and FASTA index are read
+    brc_config cfg{}; cfg.min_mapq = min_mapq; cfg.min_bq = min_bq; cfg.max_cnt = max_cnt; cfg.per_lib = per_lib; cfg.insertion_centric = ic;
+    cfg.n_libs = 0; cfg.device = std::getenv("BRC_DEVICE") ? std::atoi(std::getenv("BRC_DEVICE")) : 0;
+    const bool decode_only = std::getenv("BRC_CLI_DECODE_ONLY") != nullptr;   // test hook: exercise BGZF/BAI/region fetch without a GPU
+    int warm_rc = BRC_OK;
+    std::thread warm([&] { if (decode_only) return; brc_config c0 = cfg; c0.per_lib = 0; brc_engine *tmp = nullptr; warm_rc = brc_create(&c0, &tmp); if (tmp) brc_destroy(tmp); });
+
     BamFile bam;
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
     if (bam_path.size() > 5 && bam_path.substr(bam_path.size() - 5) == ".cram") { std::fprintf(stderr, "CRAM input is not supported by this host; convert to BAM\n"); return 1; }
     if (!bam.open(bam_path)) { std::fprintf(stderr, "Fail to open BAM file %s\n", bam_path.c_str()); return 1; }
     Fasta fa;
@@ -358,12 +418,12 @@ int main(int argc, char **argv) {
         return 1;
     }
     if (!bam.load_index(bam_path)) { std::fprintf(stderr, "BAM indexing file is not available.\n"); return 1; }
-    if (!have_fa) { std::fprintf(stderr, "A reference FASTA (-f) is required in region / site-list mode\n"); return 1; }
+    if (!have_fa && !decode_only) { std::fprintf(stderr, "A reference FASTA (-f) is required in region / site-list mode\n"); return 1; }
 
-    brc_config cfg{}; cfg.min_mapq = min_mapq; cfg.min_bq = min_bq; cfg.max_cnt = max_cnt; cfg.per_lib = per_lib; cfg.insertion_centric = ic;
-    cfg.n_libs = (int32_t)lib_names.size(); cfg.device = std::getenv("BRC_DEVICE") ? std::atoi(std::getenv("BRC_DEVICE")) : 0;
+    cfg.n_libs = (int32_t)lib_names.size();
+    warm.join();
     brc_engine *eng = nullptr;
-    int rc = brc_create(&cfg, &eng);
+    int rc = decode_only ? BRC_OK : (warm_rc != BRC_OK ? warm_rc : brc_create(&cfg, &eng));
     if (rc != BRC_OK) { std::fprintf(stderr, "brc_create: %s\n", brc_strerror(rc)); return 1; }
 
     struct Region { int tid, beg, end; bool site_list; };
@@ -421,29 +481,16 @@ int main(int argc, char **argv) {
         if (r != BRC_OK) { std::fprintf(stderr, "brc_compute: %s\n", brc_last_error(eng)); return r; }
         brc_results res{};
         if ((r = brc_get_results(eng, &res)) != BRC_OK) { std::fprintf(stderr, "brc_get_results: %s\n", brc_last_error(eng)); return r; }
-        std::vector<char> out;
-        auto emit = [&](int64_t need, auto &&fill) -> int {
-            if (need < 0) { std::fprintf(stderr, "format: %s\n", brc_last_error(eng)); return (int)need; }
-            out.resize((size_t)need + 1);
-            fill(out.data(), need + 1);
-            const double w0 = now();
-            std::fwrite(out.data(), 1, (size_t)need, stdout);
-            t_write += now() - w0;
-            return BRC_OK;
-        };
+        std::fflush(stdout);
         const double f0 = now();
         const bool argv_chain = res.n_regions > 1 && !res.regions[0].site_list_mode;   // never-cleared deletion queue: one sequential pass
         if (argv_chain) {
-            const int64_t need = brc_format_text(eng, -1, lib_ptrs.data(), nullptr, 0);
-            if (emit(need, [&](char *b, int64_t c) { brc_format_text(eng, -1, lib_ptrs.data(), b, c); }) != BRC_OK) return -1;
+            if (brc_write_text(eng, -1, 0, -1, lib_ptrs.data(), STDOUT_FILENO) < 0) { std::fprintf(stderr, "format: %s\n", brc_last_error(eng)); return -1; }
         } else {
             const int64_t WIN = 1 << 21;   // stream big regions in 2M-site windows (each formatted by several threads)
             for (int64_t g = 0; g < res.n_regions; ++g)
-                for (int64_t first = 0; first < res.regions[g].n_slots; first += WIN) {
-                    const int64_t need = brc_format_window(eng, g, first, WIN, lib_ptrs.data(), nullptr, 0);
-                    if (need == 0) continue;
-                    if (emit(need, [&](char *b, int64_t c) { brc_format_window(eng, g, first, WIN, lib_ptrs.data(), b, c); }) != BRC_OK) return -1;
-                }
+                for (int64_t first = 0; first < res.regions[g].n_slots; first += WIN)
+                    if (brc_write_text(eng, g, first, WIN, lib_ptrs.data(), STDOUT_FILENO) < 0) { std::fprintf(stderr, "format: %s\n", brc_last_error(eng)); return -1; }
         }
         t_format += now() - f0;
         return brc_reset(eng);
@@ -452,6 +499,14 @@ int main(int argc, char **argv) {
     for (size_t gi = 0; gi < regions.size(); ++gi) {
         const Region &g = regions[gi];
         const double d0 = now();
+        if (decode_only) {
+            const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
+            uint64_t voff; int64_t n = 0, psum = 0, qsum = 0;
+            if (bam.query_offset(g.tid, fbeg, voff) && bam.bz.seek(voff))
+                while (read_record(bam.bz, rec)) { if (rec.tid != g.tid || rec.pos >= fend) break; if (rec_endpos(rec) <= fbeg) continue; ++n; psum += rec.pos; for (int k = 0; k < rec.l_qseq; ++k) qsum += rec.qual[k]; }
+            std::printf("%d\t%d\t%d\t%lld\t%lld\t%lld\n", g.tid, g.beg, g.end, (long long)n, (long long)psum, (long long)qsum);
+            continue;
+        }
         if (!ref_loaded.count(g.tid)) {   // load_reference: whole chromosome
             if (!fa.fetch(bam.names[(size_t)g.tid], chrom)) { std::fprintf(stderr, "Failed to fetch %s from %s\n", bam.names[(size_t)g.tid].c_str(), fn_fa.c_str()); brc_destroy(eng); return 1; }
             rc = brc_set_reference(eng, g.tid, bam.names[(size_t)g.tid].c_str(), (int64_t)chrom.size(), 0, chrom.data(), (int64_t)chrom.size());
@@ -484,6 +539,7 @@ int main(int argc, char **argv) {
         const bool next_is_argv_chain = gi + 1 < regions.size() && !g.site_list;     // argv regions share the deletion queue: keep them in one batch
         if (gi + 1 == regions.size() || (!next_is_argv_chain && pushed > 1500000)) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
     }
+    if (decode_only) return 0;
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
     brc_destroy(eng);
     return 0;

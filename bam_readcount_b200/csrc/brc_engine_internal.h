@@ -121,7 +121,7 @@ struct brc_engine {
     int64_t warn_counts[4] = {0, 0, 0, 0};
 
     // text of the last brc_format_* call, so the usual size-query + fill pair formats only once
-    std::string fmt_cache; int64_t fmt_key[3] = {-2, -2, -2}; bool fmt_valid = false;
+    std::vector<std::string> fmt_parts; int64_t fmt_key[3] = {-2, -2, -2}; bool fmt_valid = false;
 
     int launch_count = 0;
 };

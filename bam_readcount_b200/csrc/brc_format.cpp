@@ -19,6 +19,8 @@
 #include <thread>
 #include <vector>
 
+#include <unistd.h>
+
 #include "brc_engine_internal.h"
 #include "brc_fmt_num.h"
 
@@ -149,7 +151,10 @@ void format_range(const View &V, int32_t s0, int32_t s1, const char *const *lib_
     for (int32_t s = s0; s < s1; ++s) format_site(V, s, lib_names, st, out, W, true);
 }
 
-void format_region(const brc_engine *e, int64_t g, int32_t s0, int32_t s1, const char *const *lib_names, EmitState &st, std::string &out, bool seed_from_left) {
+// Formats sites [s0, s1) of region g.  The text is appended to `parts` as one string per worker thread (in site order), so
+// nothing is concatenated or copied here.
+void format_region(const brc_engine *e, int64_t g, int32_t s0, int32_t s1, const char *const *lib_names, EmitState &st,
+                   std::vector<std::string> &parts_out, bool seed_from_left) {
     const View V(e, g);
     const brc_region &rg = *V.rg;
     s0 = std::max(s0, 0); s1 = std::min(s1, rg.n_slots);
@@ -160,48 +165,65 @@ void format_region(const brc_engine *e, int64_t g, int32_t s0, int32_t s1, const
     // The deletion queue carries state across sites.  Inside one region only the site to the left matters, so ranges can be
     // formatted independently — except in the argv loop with several regions, whose queue is never cleared (A.6): keep that sequential.
     if (!rg.site_list_mode && e->regions.size() > 1) nt = 1;
+    const size_t base = parts_out.size();
+    parts_out.resize(base + (size_t)nt);
     if (nt <= 1) {
         if (seed_from_left && s0 > 0) { Scratch W; std::string sink; format_site(V, s0 - 1, lib_names, st, sink, W, false); }
-        format_range(V, s0, s1, lib_names, st, out);
+        parts_out[base].reserve((size_t)n * 96);
+        format_range(V, s0, s1, lib_names, st, parts_out[base]);
     } else {
-        std::vector<std::string> parts((size_t)nt);
         std::vector<EmitState> states; states.reserve((size_t)nt);
         for (int t = 0; t < nt; ++t) states.emplace_back(e->n_rows);
         auto work = [&](int t) {
             const int32_t a = s0 + (int32_t)((int64_t)n * t / nt), b = s0 + (int32_t)((int64_t)n * (t + 1) / nt);
             EmitState &ls = t == 0 ? st : states[(size_t)t];
-            parts[(size_t)t].reserve((size_t)(b - a) * 420);
+            std::string &dst = parts_out[base + (size_t)t];
+            dst.reserve((size_t)(b - a) * 420);
             if ((t > 0 || seed_from_left) && a > 0) { Scratch W; std::string sink; format_site(V, a - 1, lib_names, ls, sink, W, false); }
-            format_range(V, a, b, lib_names, ls, parts[(size_t)t]);
+            format_range(V, a, b, lib_names, ls, dst);
         };
         std::vector<std::thread> th;
         for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
         work(0);
         for (auto &x : th) x.join();
-        size_t tot = out.size(); for (auto &p : parts) tot += p.size();
-        out.reserve(tot);
-        for (auto &p : parts) out += p;
-        if (nt > 1) { st.clear(); for (size_t r = 0; r < st.q.size(); ++r) { st.q[r] = states[(size_t)nt - 1].q[r]; st.q_exists[r] = states[(size_t)nt - 1].q_exists[r]; } }
+        st.clear();
+        for (size_t r = 0; r < st.q.size(); ++r) { st.q[r] = states[(size_t)nt - 1].q[r]; st.q_exists[r] = states[(size_t)nt - 1].q_exists[r]; }
     }
     if (rg.site_list_mode && s1 >= rg.n_slots) st.clear();                  // d.indel_queue_map.clear()  (R:...:605)
 }
 
-// the caller's usual pattern is a size query (buf == NULL) followed by the fill: format once, keep the text
+// the caller's usual pattern is a size query (buf == NULL) followed by the fill: format once, keep the parts
+void ensure_formatted(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const char *const *lib_names) {
+    if (e->fmt_valid && e->fmt_key[0] == k0 && e->fmt_key[1] == k1 && e->fmt_key[2] == k2) return;
+    e->fmt_parts.clear();
+    EmitState st(e->n_rows);
+    if (k1 == -1) {   // whole regions
+        if (k0 < 0) for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, 0, e->regions[(size_t)g].n_slots, lib_names, st, e->fmt_parts, false);
+        else format_region(e, k0, 0, e->regions[(size_t)k0].n_slots, lib_names, st, e->fmt_parts, false);
+    } else format_region(e, k0, (int32_t)k1, (int32_t)std::min<int64_t>(k1 + k2, 0x7fffffff), lib_names, st, e->fmt_parts, true);
+    e->fmt_key[0] = k0; e->fmt_key[1] = k1; e->fmt_key[2] = k2; e->fmt_valid = true;
+}
+int64_t parts_size(const brc_engine *e) { int64_t n = 0; for (auto &p : e->fmt_parts) n += (int64_t)p.size(); return n; }
+void release_parts(brc_engine *e) { e->fmt_valid = false; std::vector<std::string>().swap(e->fmt_parts); }
+
 int64_t serve(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const char *const *lib_names, char *buf, int64_t cap) {
-    if (!(e->fmt_valid && e->fmt_key[0] == k0 && e->fmt_key[1] == k1 && e->fmt_key[2] == k2)) {
-        e->fmt_cache.clear();
-        EmitState st(e->n_rows);
-        if (k1 == -1) {   // whole regions
-            if (k0 < 0) for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, 0, e->regions[(size_t)g].n_slots, lib_names, st, e->fmt_cache, false);
-            else format_region(e, k0, 0, e->regions[(size_t)k0].n_slots, lib_names, st, e->fmt_cache, false);
-        } else format_region(e, k0, (int32_t)k1, (int32_t)std::min<int64_t>(k1 + k2, 0x7fffffff), lib_names, st, e->fmt_cache, true);
-        e->fmt_key[0] = k0; e->fmt_key[1] = k1; e->fmt_key[2] = k2; e->fmt_valid = true;
-    }
-    const int64_t n = (int64_t)e->fmt_cache.size();
+    ensure_formatted(e, k0, k1, k2, lib_names);
+    const int64_t n = parts_size(e);
     if (buf && cap > 0) {
-        const int64_t c = std::min<int64_t>(n, cap - 1);
-        std::memcpy(buf, e->fmt_cache.data(), (size_t)c); buf[c] = 0;
-        e->fmt_valid = false; std::string().swap(e->fmt_cache);   // delivered: release the memory
+        // parallel copy of the parts into the caller's buffer (truncated at cap-1)
+        std::vector<int64_t> off(e->fmt_parts.size() + 1, 0);
+        for (size_t i = 0; i < e->fmt_parts.size(); ++i) off[i + 1] = off[i] + (int64_t)e->fmt_parts[i].size();
+        const int64_t lim = std::min<int64_t>(n, cap - 1);
+        auto copy = [&](size_t i) {
+            const int64_t a = off[i], b = std::min(off[i + 1], lim);
+            if (b > a) std::memcpy(buf + a, e->fmt_parts[i].data(), (size_t)(b - a));
+        };
+        std::vector<std::thread> th;
+        for (size_t i = 1; i < e->fmt_parts.size(); ++i) th.emplace_back(copy, i);
+        if (!e->fmt_parts.empty()) copy(0);
+        for (auto &x : th) x.join();
+        buf[lim] = 0;
+        release_parts(e);   // delivered
     }
     return n;
 }
@@ -223,4 +245,25 @@ extern "C" int64_t brc_format_window(brc_engine *e, int64_t region_index, int64_
     if (!e || region_index < 0 || region_index >= (int64_t)e->regions.size() || first < 0 || count < 0) return BRC_E_INVALID;
     if (!e->results_valid) return brc::set_error(e, BRC_E_INVALID, "format_window: no results");
     return serve(e, region_index, first, count, lib_names, buf, cap);
+}
+
+// Same text straight to a file descriptor (no intermediate buffer): region_index < 0 = all regions (first/count ignored),
+// otherwise the window [first, first+count) of that region (count < 0 = to the region's end).  Returns bytes written.
+extern "C" int64_t brc_write_text(brc_engine *e, int64_t region_index, int64_t first, int64_t count, const char *const *lib_names, int fd) {
+    if (!e || region_index >= (int64_t)e->regions.size() || first < 0) return BRC_E_INVALID;
+    if (!e->results_valid) return brc::set_error(e, BRC_E_INVALID, "write_text: no results");
+    if (region_index < 0) ensure_formatted(e, -1, -1, -1, lib_names);
+    else ensure_formatted(e, region_index, first, count < 0 ? (int64_t)0x7fffffff : count, lib_names);
+    int64_t total = 0;
+    for (auto &p : e->fmt_parts) {
+        size_t done = 0;
+        while (done < p.size()) {
+            const ssize_t w = ::write(fd, p.data() + done, p.size() - done);
+            if (w < 0) { release_parts(e); return brc::set_error(e, BRC_E_INVALID, "write_text: write() failed"); }
+            done += (size_t)w;
+        }
+        total += (int64_t)p.size();
+    }
+    release_parts(e);
+    return total;
 }

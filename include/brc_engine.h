@@ -207,6 +207,10 @@ BRC_API int64_t brc_format_text(brc_engine *e, int64_t region_index, const char 
 BRC_API int64_t brc_format_window(brc_engine *e, int64_t region_index, int64_t first, int64_t count, const char *const *lib_names,
                                   char *buf, int64_t cap);
 
+/* Same text written straight to a file descriptor (no intermediate copy).  region_index < 0: every region (first/count
+ * ignored); otherwise the window [first, first+count) of that region (count < 0: to its end).  Returns bytes written. */
+BRC_API int64_t brc_write_text(brc_engine *e, int64_t region_index, int64_t first, int64_t count, const char *const *lib_names, int fd);
+
 /* ---- device-resident path (bench "value": inputs already in HBM) -------------------------
  * brc_plan_device: fix the region geometry (host array of n_regions regions with read_lo/hi,
  * slot_base, first_pos, n_slots filled) and size the outputs.  brc_run_device: launch the
