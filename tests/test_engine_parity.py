@@ -174,3 +174,27 @@ def test_two_contigs_and_empty_region_in_one_batch():
         assert etext == otext, _first_diff(etext, otext)
         assert edump == odump, _first_diff(edump, odump)
     _ = gap
+
+
+def test_empty_batches_and_reuse_of_one_handle():
+    """compute() with nothing pushed, a region without reads, then real work on the same handle (buffers are reused)."""
+    from bam_readcount_b200.engine import Engine
+    case = cases.synthetic_case(L=5000, depth=20, seed=9, regions=((0, 1, 5000),))
+    name, clen, seq, wb = case["contigs"][0]
+    eng = Engine()
+    try:
+        eng.set_reference(0, name, clen, seq, wb)
+        res = eng.compute()
+        assert res.n_slots == 0 and eng.format_text() == ""
+        eng.reset()
+        eng.begin_region(0, 100, 200, True); eng.end_region()          # no reads pushed
+        res = eng.compute()
+        assert eng.format_text() == ""
+        want, _, _ = cases.run_oracle(case, dict(), site_list=True)
+        for _ in range(2):
+            eng.reset()
+            eng.begin_region(0, 0, 5000, True); eng.push_reads(case["batch"]); eng.end_region()
+            eng.compute()
+            assert eng.format_text() == want
+    finally:
+        eng.close()
