@@ -8,16 +8,23 @@
 //                                 + pileup_func         R:...bamreadcount.cpp:265-346   (filters, classification)
 //                                 + BasicStat::process_read  R:src/lib/bamrc/BasicStat.cpp:28-107
 //
-// Formulation (DESIGN.md §4): site-centric gather.  One thread owns one (site, library-row);
+// Formulation (DESIGN.md §2): site-centric gather.  One thread owns one (site, library-row);
 // it walks the reads overlapping its warp's 32 sites IN FILE ORDER and accumulates the 13
 // statistics of the site's primary allele in registers.  File order per key is exactly the
 // reference's accumulation order, so the four float32 sums (and the one double-rounded add)
 // are bit-identical to the CPU reference at any depth (SURVEY.md §7 hard part 1) — no
-// event tuples are ever written to HBM.  Rare keys (a second base class at a site, indel
-// alleles) go to an L2-resident record pool owned by the same thread.
+// event tuples are ever written to HBM.  The site's second base class is accumulated in shared
+// memory; rarer keys (a third base class, indel alleles) go to an L2-resident record pool owned
+// by the same thread.
 //
-// All float arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction, no
-// fast-math): the results must match the reference's x86-64 SSE arithmetic bit for bit.
+// Data movement: both kernels stage their read bytes with bulk TMA copies (cp.async.bulk ->
+// UBLKCP) that complete on mbarriers; K1 is persistent and warp-specialised (one producer warp
+// feeding a 2-stage shared-memory ring, eight consumer warps).
+//
+// Float arithmetic uses explicit round-to-nearest intrinsics and the library is built with
+// --fmad=false: results must match the reference's x86-64 SSE arithmetic bit for bit.  The two
+// shortcuts of the hot loop (reciprocal division for small integers, float<->double by bit
+// casts) are exact and checked against the IEEE intrinsics by brc_selftest_fastmath.
 #include <algorithm>
 
 #include "brc_device.cuh"
