@@ -39,4 +39,6 @@ g++ -O2 -std=c++0x -w -Iversion -I"$B" -I"$S" -I"$H" -I"$R/src/lib" \
 cp "$S/samtools" "$OUT/samtools"
 # fixtures the reference's own integration tests use (data, not source)
 mkdir -p "$OUT/test-data" && cp "$R"/test-data/* "$OUT/test-data/" && chmod -R u+w "$OUT/test-data"
+# the extracted/compiled vendor trees are only needed during the build: drop them so oracle/_ref stays small (it travels to the GPU box)
+rm -rf "$W"
 echo "build_ref.sh: built $OUT/bam-readcount and $OUT/samtools"
