@@ -44,3 +44,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(src), f"{f} reaches into oracle/"
+
+
+def test_missing_extension_fails_loudly():
+    """No silent fallback: asking for a library that is not there raises, with the build hint."""
+    from bam_readcount_b200 import engine
+    with pytest.raises(RuntimeError) as ei:
+        engine.load_library("/nonexistent/libbrc_engine.so")
+    assert "no CPU fallback" in str(ei.value)
