@@ -14,6 +14,7 @@
 #include <cstring>
 #include <fstream>
 #include <getopt.h>
+#include <deque>
 #include <map>
 #include <set>
 #include <sstream>
@@ -131,7 +132,7 @@ struct Bgzf {
         upos = (size_t)(voff & 0xFFFF);
         return true;
     }
-    uint64_t tell() const { return (block_coff << 16) | (uint64_t)upos; }
+    uint64_t tell() const { return (block_coff << 16) + (uint64_t)upos; }   // upos may equal a full 64 KiB block
     // read exactly n bytes (spanning blocks); false at EOF
     bool read(void *dst, size_t n) {
         uint8_t *d = (uint8_t *)dst;
@@ -225,6 +226,7 @@ struct BamFile {
 
 struct Rec {   // one decoded alignment (the bam1_t fields the path reads)
     int32_t tid, pos, l_qseq, nm, sm; uint16_t flag; uint8_t mapq; uint32_t n_cigar;
+    int64_t endpos;              // bam_endpos, filled by RegionFetcher
     std::vector<uint8_t> data;   // whole record body
     const uint32_t *cigar; const uint8_t *seq, *qual; std::string rg; bool has_rg;
 };
@@ -280,6 +282,57 @@ int64_t rec_endpos(const Rec &r) {   // bam_endpos
     }
     return (int64_t)r.pos + 1;
 }
+
+// ------------------------------------------------------------------------------------------
+// samfetch(in, idx, tid, fbeg, fend) for a run of regions.  The reference re-seeks through the index and
+// re-decodes up to a 16 kb linear-index window of records for every line of a site list; here consecutive regions on one
+// contig with ascending starts share ONE forward pass over the file: records still overlapping a later region wait in a
+// small window, everything else streams straight to the caller.  Each region still receives exactly the records samfetch
+// yields (tid, endpos > fbeg, pos < fend) in file order.  `next_fbeg` (start of the following region, or INT64_MAX) only
+// bounds what is retained; a caller that then asks for something else simply falls back to an index seek.
+// ------------------------------------------------------------------------------------------
+struct RegionFetcher {
+    BamFile &bam;
+    std::deque<Rec> win;          // decoded records that may overlap a later region, file order
+    std::vector<Rec> spare;       // recycled records (keeps their heap buffers)
+    bool active = false, stream_done = false, merge = true;
+    int cur_tid = -1;
+    int64_t last_fbeg = -1, keep_floor = -1, last_pos = -1;
+    uint64_t n_seeks = 0, n_decoded = 0;
+
+    explicit RegionFetcher(BamFile &b) : bam(b) { merge = std::getenv("BRC_CLI_NO_MERGE") == nullptr; }
+
+    Rec take() { if (spare.empty()) return Rec(); Rec r = std::move(spare.back()); spare.pop_back(); return r; }
+    void give(Rec &&r) { if (spare.size() < 4096) spare.push_back(std::move(r)); }
+
+    template <class Emit> void fetch(int tid, int64_t fbeg, int64_t fend, int64_t next_fbeg, Emit &&emit) {
+        uint64_t voff;
+        if (!bam.query_offset(tid, fbeg, voff)) return;
+        const bool cont = merge && active && tid == cur_tid && fbeg >= last_fbeg && fbeg >= keep_floor && voff <= bam.bz.tell();
+        if (!cont) {
+            while (!win.empty()) { give(std::move(win.back())); win.pop_back(); }
+            stream_done = false; last_pos = -1; ++n_seeks;
+            if (!bam.bz.seek(voff)) { active = false; return; }
+            active = true; cur_tid = tid;
+        }
+        last_fbeg = fbeg; keep_floor = next_fbeg >= fbeg ? next_fbeg : fbeg;      // an unsorted successor seeks anyway
+        for (const Rec &r : win) { if (r.pos >= fend) break; if (r.endpos > fbeg) emit(r); }
+        while (!stream_done && last_pos < fend) {
+            Rec r = take();
+            if (!read_record(bam.bz, r) || r.tid != tid) { stream_done = true; give(std::move(r)); break; }
+            ++n_decoded;
+            r.endpos = rec_endpos(r); last_pos = r.pos;
+            if (r.pos < fend && r.endpos > fbeg) emit(r);
+            if (r.pos >= fend || r.endpos > keep_floor) win.push_back(std::move(r)); else give(std::move(r));
+        }
+        // drop what no later region (start >= keep_floor) can overlap; order of the rest is kept
+        size_t w = 0;
+        for (size_t i = 0; i < win.size(); ++i) {
+            if (win[i].endpos > keep_floor) { if (w != i) std::swap(win[w], win[i]); ++w; }
+        }
+        while (win.size() > w) { give(std::move(win.back())); win.pop_back(); }
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // FASTA + .fai (fai_fetch of a whole chromosome, R:...:87)
@@ -470,7 +523,6 @@ int main(int argc, char **argv) {
 
     std::set<int> ref_loaded;
     std::string chrom;
-    Rec rec;
     const bool timing = std::getenv("BRC_CLI_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_decode = 0, t_compute = 0, t_format = 0, t_write = 0, t_ref = 0;
@@ -496,14 +548,18 @@ int main(int argc, char **argv) {
         return brc_reset(eng);
     };
     int64_t pushed = 0;
+    RegionFetcher fetcher(bam);
+    auto next_fbeg = [&](size_t gi) -> int64_t {   // start of the following fetch when it continues this one, else "keep nothing"
+        if (gi + 1 >= regions.size() || regions[gi + 1].tid != regions[gi].tid) return INT64_MAX;
+        return std::max<int64_t>((int64_t)regions[gi + 1].beg - 1, 0);
+    };
     for (size_t gi = 0; gi < regions.size(); ++gi) {
         const Region &g = regions[gi];
         const double d0 = now();
         if (decode_only) {
             const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
-            uint64_t voff; int64_t n = 0, psum = 0, qsum = 0;
-            if (bam.query_offset(g.tid, fbeg, voff) && bam.bz.seek(voff))
-                while (read_record(bam.bz, rec)) { if (rec.tid != g.tid || rec.pos >= fend) break; if (rec_endpos(rec) <= fbeg) continue; ++n; psum += rec.pos; for (int k = 0; k < rec.l_qseq; ++k) qsum += rec.qual[k]; }
+            int64_t n = 0, psum = 0, qsum = 0;
+            fetcher.fetch(g.tid, fbeg, fend, next_fbeg(gi), [&](const Rec &r) { ++n; psum += r.pos; for (int k = 0; k < r.l_qseq; ++k) qsum += r.qual[k]; });
             std::printf("%d\t%d\t%d\t%lld\t%lld\t%lld\n", g.tid, g.beg, g.end, (long long)n, (long long)psum, (long long)qsum);
             continue;
         }
@@ -518,27 +574,25 @@ int main(int argc, char **argv) {
         brc_begin_region(eng, g.tid, g.beg, g.end, g.site_list ? 1 : 0);
         // samfetch(in, idx, ref, d.beg-1, d.end): records with tid, endpos > max(beg-1,0), pos < end, in file order
         const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
-        uint64_t voff;
-        if (bam.query_offset(g.tid, fbeg, voff) && bam.bz.seek(voff)) {
-            while (read_record(bam.bz, rec)) {
-                if (rec.tid != g.tid || rec.pos >= fend) break;
-                if (rec_endpos(rec) <= fbeg) continue;
-                uint16_t lib = 0;
-                if (per_lib) {
-                    lib = (uint16_t)BRC_LIB_NONE;
-                    if (rec.has_rg) { auto it = rg_lb.find(rec.rg); if (it != rg_lb.end()) lib = lib_rank[it->second]; }
-                }
-                rc = brc_push_read(eng, rec.tid, rec.pos, rec.flag, rec.mapq, lib, rec.l_qseq, rec.nm, rec.sm, rec.n_cigar, rec.cigar, rec.seq, rec.qual);
-                if (rc != BRC_OK) { std::fprintf(stderr, "brc_push_read: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
-                ++pushed;
+        int push_rc = BRC_OK;
+        fetcher.fetch(g.tid, fbeg, fend, next_fbeg(gi), [&](const Rec &r) {
+            uint16_t lib = 0;
+            if (per_lib) {
+                lib = (uint16_t)BRC_LIB_NONE;
+                if (r.has_rg) { auto it = rg_lb.find(r.rg); if (it != rg_lb.end()) lib = lib_rank[it->second]; }
             }
-        }
+            const int prc = brc_push_read(eng, r.tid, r.pos, r.flag, r.mapq, lib, r.l_qseq, r.nm, r.sm, r.n_cigar, r.cigar, r.seq, r.qual);
+            if (prc != BRC_OK && push_rc == BRC_OK) push_rc = prc;
+            ++pushed;
+        });
+        if (push_rc != BRC_OK) { std::fprintf(stderr, "brc_push_read: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
         brc_end_region(eng);
         t_decode += now() - d1;
         // site-list regions are independent: flush in batches; argv regions share the deletion queue -> one batch
         const bool next_is_argv_chain = gi + 1 < regions.size() && !g.site_list;     // argv regions share the deletion queue: keep them in one batch
         if (gi + 1 == regions.size() || (!next_is_argv_chain && pushed > 1500000)) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
     }
+    if (timing) std::fprintf(stderr, "[brc timing] index seeks %llu  records decoded %llu\n", (unsigned long long)fetcher.n_seeks, (unsigned long long)fetcher.n_decoded);
     if (decode_only) return 0;
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
     brc_destroy(eng);

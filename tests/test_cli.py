@@ -137,3 +137,80 @@ def test_cli_bgzf_bai_region_fetch_matches_python_decoder(tmp_path):
         idx = b.fetch(tid, s - 2, e)          # samfetch(d.beg-1, d.end) with d.beg = s-1
         want = (tid, s - 1, e, len(idx), int(b.pos[idx].astype(np.int64).sum()), int(sum(int(b.qual[qo[i]:qo[i + 1]].astype(np.int64).sum()) for i in idx)))
         assert g == want
+
+
+def _site_list_regions(L, rng):
+    """Sorted dense single sites, overlapping / nested / repeated regions, a backwards jump and far jumps."""
+    regs = [(int(p), int(p)) for p in range(2000, 5500, 7)]
+    regs += [(6000, 6400), (6100, 6150), (6100, 6150), (6149, 6700), (6700, 6700)]
+    regs += [(3000, 3010)]                                     # backwards
+    regs += [(int(p), int(p) + int(w)) for p, w in zip(np.sort(rng.integers(7000, L - 500, 150)), rng.integers(0, 40, 150))]
+    regs += [(L - 300, L), (1, 50)]
+    return regs
+
+
+def _make_bam(case, d):
+    from oracle.oracle import REF_SAMTOOLS
+    from bam_readcount_b200 import synth
+    name, L, seq, _ = case["contigs"][0]
+    synth.write_fasta(os.path.join(d, "ref.fa"), name, np.frombuffer(seq, dtype=np.uint8))
+    synth.write_sam(os.path.join(d, "s.sam"), case["batch"], [(name, L)], n_libs=len(case["lib_names"]))
+    subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-o", os.path.join(d, "s.bam"), os.path.join(d, "s.sam")])
+    subprocess.check_call([REF_SAMTOOLS, "index", os.path.join(d, "s.bam")])
+    return os.path.join(d, "s.bam"), os.path.join(d, "ref.fa")
+
+
+def test_cli_site_list_fetch_merging_yields_samfetch_records(tmp_path):
+    """CPU: consecutive site-list lines share one forward pass over the BAM instead of one index seek
+    each; every region must still receive exactly the records samfetch yields.  Checked against the per-region seek path
+    (BRC_CLI_NO_MERGE) and against the Python decoder."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    exe = _cli()
+    case = cases.synthetic_case(L=60000, depth=30, seed=77, regions=((0, 1, 60000),), site_list=True)
+    bam, _ = _make_bam(case, str(tmp_path))
+    regs = _site_list_regions(60000, np.random.default_rng(5))
+    sl = tmp_path / "sites"
+    sl.write_text("".join(f"chr1\t{s}\t{e}\n" for s, e in regs))
+    outs, stats = [], []
+    for extra in ({}, {"BRC_CLI_NO_MERGE": "1"}):
+        p = subprocess.run([exe, "-l", str(sl), bam], capture_output=True, env=dict(os.environ, BRC_CLI_DECODE_ONLY="1", BRC_CLI_TIMING="1", **extra))
+        assert p.returncode == 0, p.stderr.decode()
+        outs.append(p.stdout.decode())
+        line = [ln for ln in p.stderr.decode().splitlines() if "index seeks" in ln][0].split()
+        stats.append((int(line[4]), int(line[7])))
+    assert outs[0] == outs[1]
+    assert stats[0][0] < 20 and stats[1][0] == len(regs)          # a handful of seeks instead of one per line
+    assert stats[0][1] * 20 < stats[1][1]                          # and far fewer records decoded
+    b = case["batch"]
+    qo = b.qual_off.astype(np.int64)
+    got = [tuple(int(x) for x in line.split("\t")) for line in outs[0].strip().splitlines()]
+    for (s, e), g in zip(regs, got):
+        idx = b.fetch(0, max(s - 2, 0), e)
+        want = (0, s - 1, e, len(idx), int(b.pos[idx].astype(np.int64).sum()), int(sum(int(b.qual[qo[i]:qo[i + 1]].astype(np.int64).sum()) for i in idx)))
+        assert g == want, (s, e)
+
+
+@pytest.mark.gpu
+def test_cli_dense_site_list_matches_oracle(tmp_path):
+    """A few hundred site-list lines (dense, overlapping, nested, repeated, out of order) through the merged fetch, the
+    engine and the emitter, against the CPU oracle run region by region like the reference's -l loop."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    exe = _cli()
+    regs = _site_list_regions(60000, np.random.default_rng(5))
+    case = cases.synthetic_case(L=60000, depth=30, seed=77, regions=tuple((0, s, e) for s, e in regs), site_list=True)
+    bam, ref = _make_bam(case, str(tmp_path))
+    sl = tmp_path / "sites"
+    sl.write_text("".join(f"chr1\t{s}\t{e}\n" for s, e in regs))
+    for fl, argv in ((dict(min_mapq=20, min_bq=20), ["-q", "20", "-b", "20"]), (dict(per_lib=True), ["-p"])):
+        want, _, _ = cases.run_oracle(case, fl, site_list=True)
+        outs = []
+        for extra in ({}, {"BRC_CLI_NO_MERGE": "1"}):
+            p = subprocess.run([exe, "-w", "0", "-f", ref] + argv + ["-l", str(sl), bam], capture_output=True, env=dict(os.environ, **extra))
+            assert p.returncode == 0, p.stderr.decode()[-2000:]
+            outs.append(p.stdout.decode("latin-1"))
+        assert outs[0] == outs[1]
+        assert outs[0] == want
