@@ -536,7 +536,10 @@ int main(int argc, char **argv) {
         std::fflush(stdout);
         const double f0 = now();
         const bool argv_chain = res.n_regions > 1 && !res.regions[0].site_list_mode;   // never-cleared deletion queue: one sequential pass
-        if (argv_chain) {
+        int64_t total_slots = 0;
+        for (int64_t g = 0; g < res.n_regions; ++g) total_slots += res.regions[g].n_slots;
+        const bool many_small = res.n_regions > 1 && total_slots <= (int64_t(1) << 22);  // a site list: all regions in one formatting pass
+        if (argv_chain || many_small) {
             if (brc_write_text(eng, -1, 0, -1, lib_ptrs.data(), STDOUT_FILENO) < 0) { std::fprintf(stderr, "format: %s\n", brc_last_error(eng)); return -1; }
         } else {
             const int64_t WIN = 1 << 21;   // stream big regions in 2M-site windows (each formatted by several threads)

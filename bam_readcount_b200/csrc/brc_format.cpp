@@ -192,14 +192,49 @@ void format_region(const brc_engine *e, int64_t g, int32_t s0, int32_t s1, const
     if (rg.site_list_mode && s1 >= rg.n_slots) st.clear();                  // d.indel_queue_map.clear()  (R:...:605)
 }
 
+// Many regions of the -l loop (a site list is typically thousands of one-base lines): every region starts with an empty
+// deletion queue (R:...:605), so whole regions are dealt to worker threads — one output string per thread, regions in order.
+// Returns false (nothing done) when the batch is not of that shape.
+bool format_many_site_list_regions(const brc_engine *e, const char *const *lib_names, std::vector<std::string> &parts_out) {
+    const size_t nr = e->regions.size();
+    if (nr < 2) return false;
+    int64_t total = 0;
+    for (const brc_region &rg : e->regions) { if (!rg.site_list_mode) return false; total += rg.n_slots; }
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::min<int64_t>({(int64_t)(hw ? hw : 1), (int64_t)32, total / 16384 + 1});
+    std::vector<size_t> cut((size_t)nt + 1, nr);
+    cut[0] = 0;
+    { int64_t acc = 0; int t = 1; for (size_t g = 0; g < nr && t < nt; ++g) { acc += e->regions[g].n_slots; while (t < nt && acc >= total * t / nt) cut[(size_t)t++] = g + 1; } }
+    const size_t base = parts_out.size();
+    parts_out.resize(base + (size_t)nt);
+    auto work = [&](int t) {
+        EmitState st(e->n_rows);
+        std::string &dst = parts_out[base + (size_t)t];
+        int64_t slots = 0;
+        for (size_t g = cut[(size_t)t]; g < cut[(size_t)t + 1]; ++g) slots += e->regions[g].n_slots;
+        dst.reserve((size_t)slots * 200);
+        for (size_t g = cut[(size_t)t]; g < cut[(size_t)t + 1]; ++g) {
+            const View V(e, (int64_t)g);
+            format_range(V, 0, V.rg->n_slots, lib_names, st, dst);
+            st.clear();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    return true;
+}
+
 // the caller's usual pattern is a size query (buf == NULL) followed by the fill: format once, keep the parts
 void ensure_formatted(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const char *const *lib_names) {
     if (e->fmt_valid && e->fmt_key[0] == k0 && e->fmt_key[1] == k1 && e->fmt_key[2] == k2) return;
     e->fmt_parts.clear();
     EmitState st(e->n_rows);
     if (k1 == -1) {   // whole regions
-        if (k0 < 0) for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, 0, e->regions[(size_t)g].n_slots, lib_names, st, e->fmt_parts, false);
-        else format_region(e, k0, 0, e->regions[(size_t)k0].n_slots, lib_names, st, e->fmt_parts, false);
+        if (k0 < 0 && !format_many_site_list_regions(e, lib_names, e->fmt_parts))
+            for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, 0, e->regions[(size_t)g].n_slots, lib_names, st, e->fmt_parts, false);
+        if (k0 >= 0) format_region(e, k0, 0, e->regions[(size_t)k0].n_slots, lib_names, st, e->fmt_parts, false);
     } else format_region(e, k0, (int32_t)k1, (int32_t)std::min<int64_t>(k1 + k2, 0x7fffffff), lib_names, st, e->fmt_parts, true);
     e->fmt_key[0] = k0; e->fmt_key[1] = k1; e->fmt_key[2] = k2; e->fmt_valid = true;
 }
