@@ -410,6 +410,7 @@ int parse_region(const BamFile &bam, const std::string &s, int &tid, int &beg, i
 }  // namespace
 
 int main(int argc, char **argv) {
+    const double t_main0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     int min_mapq = 0, min_bq = 0, max_cnt = 10000000; bool per_lib = false, ic = false; long long max_warn = -1;
     std::string fn_pos, fn_fa, dist_arg;
     static option lo[] = {{"help", 0, 0, 'h'}, {"version", 0, 0, 'v'}, {"min-mapping-quality", 1, 0, 'q'}, {"min-base-quality", 1, 0, 'b'},
@@ -551,6 +552,7 @@ int main(int argc, char **argv) {
         return brc_reset(eng);
     };
     int64_t pushed = 0;
+    const double t_loop0 = now();
     RegionFetcher fetcher(bam);
     auto next_fbeg = [&](size_t gi) -> int64_t {   // start of the following fetch when it continues this one, else "keep nothing"
         if (gi + 1 >= regions.size() || regions[gi + 1].tid != regions[gi].tid) return INT64_MAX;
@@ -598,6 +600,8 @@ int main(int argc, char **argv) {
     if (timing) std::fprintf(stderr, "[brc timing] index seeks %llu  records decoded %llu\n", (unsigned long long)fetcher.n_seeks, (unsigned long long)fetcher.n_decoded);
     if (decode_only) return 0;
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
+    const double t_d0 = now();
     brc_destroy(eng);
+    if (timing) std::fprintf(stderr, "[brc timing] startup (CUDA context, header, index) %.3fs  teardown %.3fs\n", t_loop0 - t_main0, now() - t_d0);
     return 0;
 }

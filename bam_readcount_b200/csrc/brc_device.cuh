@@ -143,7 +143,17 @@ struct PileupParams {
     int64_t tile_begin;    // this launch covers tiles [tile_begin, tile_begin + tile_count)
     int64_t tile_count;
     ResultsDev res;
+    // deep-site kernel (brc_kernels.cu): candidate tiles (<= DEEP_MAX_SITES sites); a candidate whose read window holds at
+    // least deep_min_reads reads is computed by deep_site_kernel and skipped by pileup_kernel
+    const int32_t *deep_tiles;
+    int32_t n_deep;
+    int32_t deep_min_reads;
 };
+
+constexpr int DEEP_MAX_SITES = 2;
+constexpr int DEEP_THREADS = 256;
+// one owner thread per (site, library row, statistic): the tile qualifies only if they fit one CTA
+__host__ __device__ inline bool deep_shape_ok(int n_sites, int n_rows) { return n_sites <= DEEP_MAX_SITES && n_sites * n_rows * N_STATS <= DEEP_THREADS; }
 
 struct PrecomputeParams {
     ReadsDev reads;
@@ -164,6 +174,7 @@ cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tile
 cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s);
 cudaError_t launch_ref_encode(const char *d_ascii, uint8_t *d_code, int64_t n, cudaStream_t s);
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s);
+cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s);   // no-op when p.n_deep == 0
 cudaError_t launch_fastmath_selftest(int max_b, unsigned long long *d_bad, cudaStream_t s);
 
 }  // namespace brc

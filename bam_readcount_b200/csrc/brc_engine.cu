@@ -323,7 +323,8 @@ int brc_end_region(brc_engine *e) {
 // geometry + launches
 // ---------------------------------------------------------------------------------------------
 static int build_geometry(brc_engine *e, const brc_region *regs, int64_t n_regions) {
-    e->tiles.clear(); e->regions_dev.clear();
+    e->tiles.clear(); e->regions_dev.clear(); e->deep_tiles.clear();
+    if (const char *ov = std::getenv("BRC_DEEP_MIN_READS")) e->deep_min_reads = std::max(1, std::atoi(ov));   // test hook (0x7fffffff disables the deep-site kernel)
     int64_t n_slots = 0;
     for (int64_t g = 0; g < n_regions; ++g) {
         const brc_region &r = regs[g];
@@ -335,8 +336,11 @@ static int build_geometry(brc_engine *e, const brc_region *regs, int64_t n_regio
         d.tile_base = (int64_t)e->tiles.size(); d.read_lo = r.read_lo; d.read_hi = r.read_hi;
         e->regions_dev.push_back(d);
         if (r.slot_base != n_slots) return set_error(e, BRC_E_INVALID, "regions: slot_base must be the running sum of n_slots");
-        for (int32_t o = 0; o < r.n_slots; o += TILE)
-            e->tiles.push_back(TileInfo{r.first_pos + o, std::min(TILE, r.n_slots - o), r.slot_base + o});
+        for (int32_t o = 0; o < r.n_slots; o += TILE) {
+            const int32_t tn = std::min(TILE, r.n_slots - o);
+            if (r.read_hi - r.read_lo >= e->deep_min_reads && deep_shape_ok(tn, e->n_rows)) e->deep_tiles.push_back((int32_t)e->tiles.size());
+            e->tiles.push_back(TileInfo{r.first_pos + o, tn, r.slot_base + o});
+        }
         n_slots += r.n_slots;
     }
     e->n_slots = n_slots;
@@ -352,6 +356,7 @@ static int alloc_outputs(brc_engine *e, int64_t n_reads_cap) {
     CU(e->d_tile_lo.reserve(nt * 4), "cudaMalloc(tile_lo)");
     CU(e->d_tile_hi.reserve(nt * 4), "cudaMalloc(tile_hi)");
     CU(e->d_regions.reserve(std::max<size_t>(e->regions_dev.size(), 1) * sizeof(RegionDev)), "cudaMalloc(regions)");
+    CU(e->d_deep_tiles.reserve(std::max<size_t>(e->deep_tiles.size(), 1) * 4), "cudaMalloc(deep_tiles)");
     CU(e->d_ncover.reserve(rs1 * 4), "cudaMalloc(ncover)");
     CU(e->d_npass.reserve(rs1 * 4), "cudaMalloc(npass)");
     CU(e->d_flags.reserve(rs1), "cudaMalloc(flags)");
@@ -392,6 +397,8 @@ static int upload_geometry(brc_engine *e, cudaStream_t s) {
         CU(cudaMemcpyAsync(e->d_tiles.p, e->tiles.data(), e->tiles.size() * sizeof(TileInfo), cudaMemcpyHostToDevice, s), "H2D tiles");
     if (!e->regions_dev.empty())
         CU(cudaMemcpyAsync(e->d_regions.p, e->regions_dev.data(), e->regions_dev.size() * sizeof(RegionDev), cudaMemcpyHostToDevice, s), "H2D regions");
+    if (!e->deep_tiles.empty())
+        CU(cudaMemcpyAsync(e->d_deep_tiles.p, e->deep_tiles.data(), e->deep_tiles.size() * 4, cudaMemcpyHostToDevice, s), "H2D deep tiles");
     return BRC_OK;
 }
 
@@ -407,6 +414,7 @@ static void make_params(brc_engine *e, const int32_t *d_region_of_read, Precompu
     P1.seq_off = e->dev_reads.seq_off; P1.qual_off = e->dev_reads.qual_off;
     P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size(); P1.tile_begin = 0; P1.tile_count = P1.n_tiles;
     P1.res = results_dev(e);
+    P1.deep_tiles = e->deep_tiles.empty() ? nullptr : e->d_deep_tiles.as<int32_t>(); P1.n_deep = (int32_t)e->deep_tiles.size(); P1.deep_min_reads = e->deep_min_reads;
 }
 
 // K(init) + K0 + K1 on stream s.  Returns BRC_E_OVERFLOW (after syncing) if the secondary pool was too small.
@@ -420,6 +428,7 @@ static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStrea
     CU(launch_precompute(P0, s), "launch read_precompute"); if (P0.reads.n_reads) e->launch_count++;
     CU(cudaEventRecord(e->ev[1], s), "event");
     CU(launch_pileup(P1, s), "launch pileup"); if (P1.n_tiles) e->launch_count++;
+    CU(launch_deep_sites(P1, s), "launch deep_sites"); if (P1.n_deep) e->launch_count++;
     CU(cudaEventRecord(e->ev[2], s), "event");
     if (check_overflow) {
         int32_t cnt = 0;
@@ -563,6 +572,7 @@ static int compute_pipelined(brc_engine *e) {
         if (tile_to > tile_done) {
             P1.tile_begin = tile_done; P1.tile_count = tile_to - tile_done;
             CU(launch_pileup(P1, sk), "launch pileup"); e->launch_count++;
+            CU(launch_deep_sites(P1, sk), "launch deep_sites"); if (P1.n_deep) e->launch_count++;
             CU(cudaEventRecord(e->pipe_ev[2 * c + 1], sk), "event");
             // ---- D2H of the finished slots ----
             CU(cudaStreamWaitEvent(e->s_out, e->pipe_ev[2 * c + 1], 0), "wait");

@@ -100,6 +100,8 @@ struct brc_engine {
 
     // geometry (push path or plan_device)
     std::vector<brc::TileInfo> tiles;
+    std::vector<int32_t> deep_tiles;   // tiles of <= DEEP_MAX_SITES sites in regions with many reads: candidates of the deep-site kernel
+    int32_t deep_min_reads = 2048;     // a candidate tile with at least this many reads in its window takes the deep-site kernel
     std::vector<brc::RegionDev> regions_dev;
     int64_t n_slots = 0;
     int64_t sec_cap = 0;
@@ -107,7 +109,7 @@ struct brc_engine {
 
     // device buffers
     brc::DevBuf d_in[14];            // uploaded read arrays (push path)
-    brc::DevBuf d_desc, d_tiles, d_tile_lo, d_tile_hi, d_regions;
+    brc::DevBuf d_desc, d_tiles, d_tile_lo, d_tile_hi, d_regions, d_deep_tiles;
     brc::DevBuf d_ncover, d_npass, d_flags, d_pbase, d_sec_head, d_pstats;
     brc::DevBuf d_sec_count, d_sec_next, d_sec_kind, d_sec_len, d_sec_read, d_sec_qpos, d_sec_stats, d_warn;
     brc::ReadsDev dev_reads{};       // what the kernels read (push path: d_in; device path: caller's pointers)

@@ -482,7 +482,7 @@ __device__ __forceinline__ float div_small(float a, float b, float rcp) {
 }
 
 // One (site, read) event's contributions — the body of BasicStat::process_read (R:BasicStat.cpp:28-107).
-struct Terms { float q2term, d3pterm; double posterm; };
+struct Terms { float q2term, d3pterm, posf; double posterm; };   // posterm == 1.0 - (double)posf
 __device__ __forceinline__ Terms event_terms(bool fast, int qpos, int q2pos, int tpi, int lclip, int clen, float fl, float fclen,
                                              float rcp_l, float rcp_c) {
     Terms t;
@@ -494,12 +494,14 @@ __device__ __forceinline__ Terms event_terms(bool fast, int qpos, int q2pos, int
         t.q2term = (q2pos < 0 || q2pos == tpi) ? t.d3pterm : div_small((float)abs(qpos - q2pos), fl, rcp_l);
         // |(qpos-lclip) - clen/2| / (clen/2)  ==  |2(qpos-lclip) - clen| / clen   (numerator and denominator exact)
         const float f = div_small((float)abs(2 * (qpos - lclip) - clen), fclen, rcp_c);
+        t.posf = f;
         t.posterm = __dsub_rn(1.0, f32_to_f64_nonneg(f));
     } else {
         t.q2term = __fdiv_rn((float)abs(qpos - q2pos), fl);
         t.d3pterm = __fdiv_rn(a_3p, fl);
         const float rc = __fmul_rn(fclen, 0.5f);
         const float f = __fdiv_rn(fabsf(__fsub_rn((float)(qpos - lclip), rc)), rc);
+        t.posf = f;
         t.posterm = __dsub_rn(1.0, (double)f);
     }
     return t;
@@ -808,6 +810,8 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
                 // -p on a tile of <= 32 sites (site lists, deep panels): the 8 consumer warps take 8 LIBRARIES of the
                 // same sites instead of 8 site ranges, so one staged chunk serves 8 rows
                 narrow = PER_LIB && ti.n <= 32;
+                // deep narrow tiles (a single site under thousands of reads) belong to deep_site_kernel
+                if (P.n_deep > 0 && deep_shape_ok(ti.n, P.res.n_rows) && hi - lo >= P.deep_min_reads) continue;
                 if (narrow && (row % N_CONSUMER_WARPS) != 0) continue;
             }
             int32_t r0 = lo;
@@ -924,6 +928,203 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
     const size_t smem = sizeof(PileupSmem);
     if (p.per_lib) pileup_kernel<true><<<grid, K1_THREADS, smem, s>>>(p);
     else pileup_kernel<false><<<grid, K1_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1-deep: one CTA per DEEP tile — a tile of <= DEEP_MAX_SITES sites (a site-list line: the site and its left neighbour)
+// whose read window holds thousands of reads (amplicon / panel depth).  pileup_kernel would walk those reads one by one in
+// a single lane per (site, library); here the per-event work is done read-parallel and only the accumulation is ordered:
+//   phase 1  thread = read (256 per block, file order): coverage, resolve_cigar2, filters, base class, the 13 terms of
+//            BasicStat::process_read; passing events are written to shared memory, stably partitioned by (site, library)
+//            (warp match + per-warp counts), so each group's events stay in file order;
+//   phase 2  thread = (site, library, statistic): walks its group's events in order and adds its one term to a register —
+//            the same sequence of float32 / double-rounded additions as the reference, so results stay bit-identical.
+//            The first passing base class is the primary allele (registers -> pstats); events of any other key (another
+//            base class, an indel allele) are handed, in order, to rare_event by the group's statistic-0 thread.
+// Integer statistics go through the same ordered loop: it keeps one code path and costs one predicated add.
+// ---------------------------------------------------------------------------------------------
+constexpr int DEEP_EVENTS = DEEP_THREADS * DEEP_MAX_SITES;
+constexpr int DEEP_GROUPS = DEEP_THREADS / N_STATS;          // upper bound of n_sites * n_rows (deep_shape_ok)
+constexpr int DEEP_WARPS = DEEP_THREADS / 32;
+struct __align__(16) DeepSmem {
+    uint32_t term[N_STATS][DEEP_EVENTS + 1];   // +1: the 13 owners of a group read one column -> 13 different banks
+    uint32_t meta[DEEP_EVENTS];                // base class [0:3) | bit3 has indel | bit4 has base part | bq << 8
+    int32_t eread[DEEP_EVENTS];                // read index
+    int32_t eqpos[DEEP_EVENTS];
+    int32_t eindel[DEEP_EVENTS];
+    uint32_t wcnt[DEEP_WARPS][DEEP_GROUPS + 1];   // phase 1: events of group g in warp w -> exclusive offset inside the group
+    uint32_t gcnt[DEEP_GROUPS + 1], gbase[DEEP_GROUPS + 1];
+    uint32_t ncover[DEEP_GROUPS + 1], npass[DEEP_GROUPS + 1];
+    int32_t first_libless[DEEP_MAX_SITES];        // -p: first covering read without a library (nothing after it counts)
+};
+
+template <bool PER_LIB>
+__global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P) {
+    __shared__ DeepSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int32_t tile = P.deep_tiles[blockIdx.x];
+    if (tile < P.tile_begin || tile >= P.tile_begin + P.tile_count) return;
+    const TileInfo ti = P.tiles[tile];
+    int32_t lo = P.tile_lo[tile], hi = P.tile_hi[tile];
+    if (lo >= hi) { lo = 0; hi = 0; }
+    const int n_rows = P.res.n_rows;
+    if (!deep_shape_ok(ti.n, n_rows) || hi - lo < P.deep_min_reads) return;   // pileup_kernel computes it (same predicate)
+    const int G = ti.n * n_rows;
+
+    for (int i = tid; i <= DEEP_GROUPS; i += DEEP_THREADS) { sm.ncover[i] = 0u; sm.npass[i] = 0u; }
+    if (tid < DEEP_MAX_SITES) sm.first_libless[tid] = 0x7fffffff;
+
+    // phase-2 owner state
+    const bool owner = tid < G * N_STATS;
+    const int og = tid / N_STATS, oj = tid - og * N_STATS;   // group = site * n_rows + row
+    uint32_t acc_u = 0u; float acc_f = 0.0f; double acc_d = 0.0;
+    uint32_t pbase = NO_BASE; int32_t sec_head = -1;
+    uint32_t warn_nm = 0u, warn_sm = 0u;
+    __syncthreads();
+
+    for (int32_t blk = lo; blk < hi; blk += DEEP_THREADS) {
+        const int32_t r = blk + tid;
+        const bool valid = r < hi;
+        // ---- phase 1a: coverage; -p: the first covering read without a library ----
+        int4 q0 = make_int4(0, 0, 0, 0);
+        if (valid) q0 = *reinterpret_cast<const int4 *>(&P.desc[r]);
+        const uint32_t fm = (uint32_t)q0.z, lib = (uint32_t)q0.w & 0xFFFFu;
+        bool cover[DEEP_MAX_SITES];
+#pragma unroll
+        for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
+            const int32_t site = ti.pos0 + sg;
+            cover[sg] = valid && sg < ti.n && site >= q0.x && site < q0.y;
+            if (PER_LIB && cover[sg] && lib == LIB_NONE) atomicMin(&sm.first_libless[sg], r);
+        }
+        for (int i = tid; i < DEEP_WARPS * (DEEP_GROUPS + 1); i += DEEP_THREADS) (&sm.wcnt[0][0])[i] = 0u;
+        __syncthreads();
+        // ---- phase 1b: the events of this read ----
+        bool has[DEEP_MAX_SITES]; int grp[DEEP_MAX_SITES]; uint32_t w[DEEP_MAX_SITES][N_STATS];
+        uint32_t emeta[DEEP_MAX_SITES]; int eq[DEEP_MAX_SITES], ei[DEEP_MAX_SITES];
+        ReadDesc d; bool d_loaded = false;
+#pragma unroll
+        for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
+            has[sg] = false; grp[sg] = 0; emeta[sg] = 0u; eq[sg] = 0; ei[sg] = 0;
+            if (!cover[sg]) continue;
+            uint32_t row = 0u;
+            if (PER_LIB) {
+                if (lib == LIB_NONE || lib >= (uint32_t)n_rows) continue;
+                if (r > sm.first_libless[sg]) continue;          // pileup_func returned early at this site (R:...:281-284)
+                row = lib;
+            }
+            const int g = sg * n_rows + (int)row;
+            atomicAdd(&sm.ncover[g], 1u);
+            const int32_t site = ti.pos0 + sg;
+            if (!d_loaded) { d = P.desc[r]; d_loaded = true; }
+            int qpos, indel = 0;
+            if (fm & FM_SIMPLE) qpos = site - d.pos + (int)d.cig;
+            else {
+                const int3 rr = resolve_general(P.cigar + d.cig, d.n_cigar, d.pos, site);
+                if (rr.z) continue;
+                qpos = rr.x; indel = rr.y;
+            }
+            const uint32_t mapq = (fm >> 16) & 0xFFu;
+            if ((int)mapq < P.min_mapq) continue;
+            const uint32_t bq = P.qual[P.qual_off[r] + (uint32_t)qpos];
+            if ((int)bq < P.min_bq) continue;
+            if (fm & FLAG_FILTER) continue;
+            atomicAdd(&sm.npass[g], 1u);
+            const bool base_part = !(indel > 0 && P.insertion_centric);
+            const uint32_t nw = (indel != 0 ? 1u : 0u) + (base_part ? 1u : 0u);   // process_read calls that warn
+            warn_nm += nw * ((fm >> 25) & 1u); warn_sm += nw * ((fm >> 26) & 1u);
+            const uint32_t byte = P.seq[P.seq_off[r] + ((uint32_t)qpos >> 1)];
+            const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
+            const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, d.rcp_l, d.rcp_clen);
+            const uint32_t plus = (fm & 16u) ? 0u : 1u;
+            const bool has_q2 = d.q2 > -1;
+            w[sg][0] = 1u; w[sg][1] = mapq; w[sg][2] = bq; w[sg][3] = (uint32_t)d.se; w[sg][4] = plus; w[sg][5] = 1u - plus;
+            w[sg][6] = __float_as_uint(t.posf); w[sg][7] = __float_as_uint(d.nmfrac); w[sg][8] = (uint32_t)d.mmq;
+            w[sg][9] = has_q2 ? 1u : 0u; w[sg][10] = has_q2 ? __float_as_uint(t.q2term) : 0u;   // + 0.0f leaves the sum unchanged
+            w[sg][11] = (uint32_t)d.clen; w[sg][12] = __float_as_uint(t.d3pterm);
+            emeta[sg] = base | (indel != 0 ? 8u : 0u) | (base_part ? 16u : 0u) | (bq << 8);
+            eq[sg] = qpos; ei[sg] = indel; has[sg] = true; grp[sg] = g;
+        }
+        // stable partition by group: rank inside the warp, then warp offsets, then group bases
+        int rank[DEEP_MAX_SITES];
+#pragma unroll
+        for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
+            const unsigned m = __match_any_sync(0xffffffffu, has[sg] ? grp[sg] : -1 - lane);
+            rank[sg] = __popc(m & ((1u << lane) - 1u));
+            if (has[sg] && rank[sg] == 0) sm.wcnt[warp][grp[sg]] = (uint32_t)__popc(m);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t tot = 0u;
+            if (lane < G) for (int wv = 0; wv < DEEP_WARPS; ++wv) { const uint32_t c = sm.wcnt[wv][lane]; sm.wcnt[wv][lane] = tot; tot += c; }
+            uint32_t incl = tot;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane < G) { sm.gcnt[lane] = tot; sm.gbase[lane] = incl - tot; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
+            if (!has[sg]) continue;
+            const uint32_t slot = sm.gbase[grp[sg]] + sm.wcnt[warp][grp[sg]] + (uint32_t)rank[sg];
+#pragma unroll
+            for (int k = 0; k < N_STATS; ++k) sm.term[k][slot] = w[sg][k];
+            sm.meta[slot] = emeta[sg]; sm.eread[slot] = r; sm.eqpos[slot] = eq[sg]; sm.eindel[slot] = ei[sg];
+        }
+        __syncthreads();
+        // ---- phase 2: ordered accumulation ----
+        if (owner) {
+            const uint32_t b0 = sm.gbase[og], n = sm.gcnt[og];
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t slot = b0 + i;
+                const uint32_t m = sm.meta[slot];
+                if ((m & 8u) && oj == 0) {
+                    const int indel = sm.eindel[slot];
+                    sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
+                }
+                if (!(m & 16u)) continue;
+                const uint32_t base = m & 7u;
+                if (pbase == NO_BASE) pbase = base;
+                if (base == pbase) {
+                    const uint32_t x = sm.term[oj][slot];
+                    if (oj == 6) acc_d = round_to_f32_precision(__dadd_rn(acc_d, __dsub_rn(1.0, (double)__uint_as_float(x))));
+                    else if (oj == 7 || oj == 10 || oj == 12) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
+                    else acc_u += x;
+                } else if (oj == 0) {
+                    sec_head = rare_event(P, sec_head, (int)base, 0, sm.eread[slot], sm.eqpos[slot], m >> 8, false);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- emit: the layout site_emit writes ----
+    if (owner) {
+        const ResultsDev &R = P.res;
+        const int sg = og / n_rows, row = og - sg * n_rows;
+        const int64_t idx = (int64_t)row * R.n_slots + ti.slot0 + sg;
+        const int64_t stride = (int64_t)R.n_rows * R.n_slots;
+        uint32_t v;
+        if (oj == 6) v = __float_as_uint(__double2float_rn(acc_d));
+        else if (oj == 7 || oj == 10 || oj == 12) v = __float_as_uint(acc_f);
+        else v = acc_u;
+        R.pstats[(int64_t)oj * stride + idx] = v;
+        if (oj == 0) {
+            R.ncover[idx] = sm.ncover[og]; R.npass[idx] = sm.npass[og];
+            R.flags[idx] = (uint8_t)((PER_LIB && sm.first_libless[sg] != 0x7fffffff) ? 1u : 0u);
+            R.pbase[idx] = (uint8_t)pbase; R.sec_head[idx] = sec_head;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { warn_sm += __shfl_xor_sync(0xffffffffu, warn_sm, o); warn_nm += __shfl_xor_sync(0xffffffffu, warn_nm, o); }
+    if (lane == 0) {
+        if (warn_sm) atomicAdd(P.res.warn + 0, (unsigned long long)warn_sm);
+        if (warn_nm) atomicAdd(P.res.warn + 1, (unsigned long long)warn_nm);
+    }
+}
+
+cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s) {
+    if (p.n_deep <= 0 || p.tile_count <= 0) return cudaSuccess;
+    if (p.per_lib) deep_site_kernel<true><<<(unsigned)p.n_deep, DEEP_THREADS, 0, s>>>(p);
+    else deep_site_kernel<false><<<(unsigned)p.n_deep, DEEP_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

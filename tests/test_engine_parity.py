@@ -42,6 +42,35 @@ def test_engine_accumulators_match_oracle_bit_exact(job):
     assert (ewarn[0], ewarn[1], ewarn[3]) == owarn
 
 
+@pytest.mark.parametrize("job", JOBS, ids=[j[0] for j in JOBS])
+def test_deep_site_kernel_matches_oracle_bit_exact(job, monkeypatch):
+    """Every tile of <= 2 sites forced through deep_site_kernel (read-parallel events, ordered accumulation) instead of
+    pileup_kernel: same raw accumulators, warning counters and text.  (By default only tiles under >= 2048 reads take it:
+    the deep-* jobs above already do.)"""
+    monkeypatch.setenv("BRC_DEEP_MIN_READS", "1")
+    _, getter, flags, site_list, golden = job
+    case = getter()
+    _, odump, owarn = cases.run_oracle(case, flags, site_list=True)
+    _, edump, ewarn, _ = cases.run_engine(case, flags, site_list=True, want_dump=True)
+    assert edump == odump, _first_diff(edump, odump)
+    assert (ewarn[0], ewarn[1], ewarn[3]) == owarn
+    text, _, _, _ = cases.run_engine(case, flags, site_list=site_list, want_dump=False)
+    want = cases.load_golden_text(golden)
+    assert text == want, _first_diff(text, want)
+
+
+def test_deep_site_kernel_is_what_runs_on_a_deep_panel(monkeypatch):
+    """50 000x on one site, 8 libraries: identical results with the deep-site kernel (default) and with it disabled."""
+    case = cases.deep_case(n_sites=2, depth=20000, seed=9)
+    fl = dict(per_lib=True, max_cnt=100000000)
+    _, d1, w1, _ = cases.run_engine(case, fl, site_list=True, want_dump=True)
+    monkeypatch.setenv("BRC_DEEP_MIN_READS", "2147483647")
+    _, d2, w2, _ = cases.run_engine(case, fl, site_list=True, want_dump=True)
+    assert d1 == d2 and tuple(w1) == tuple(w2)
+    _, od, _ = cases.run_oracle(case, fl, site_list=True)
+    assert d1 == od
+
+
 def test_exact_arithmetic_shortcuts_match_ieee_intrinsics():
     """K1 replaces __fdiv_rn by a reciprocal + one FMA correction and float<->double conversions by bit
     casts for read lengths <= 2048; every (numerator, divisor) pair it can see must agree with IEEE."""

@@ -20,7 +20,7 @@ for out in ("/dev/null", d + "/out.txt"):
     with open(out, "wb") as fh:
         p = subprocess.run([exe, "-w", "0", "-q", "20", "-b", "20", "-f", d + "/ref.fa", d + "/s.bam", f"chr1:1-{L}"], stdout=fh, stderr=subprocess.PIPE, env=env)
     dt = time.time() - t0
-    print(f"brc-readcount -> {out}: {dt:.2f}s  ({L/dt:.3e} positions/s) rc={p.returncode}", p.stderr.decode().strip().splitlines()[-1])
+    print(f"brc-readcount -> {out}: {dt:.2f}s  ({L/dt:.3e} positions/s) rc={p.returncode}", " | ".join(p.stderr.decode().strip().splitlines()[-3:]))
 t0 = time.time()
 with open(d + "/ref_out.txt", "wb") as fh:
     subprocess.run([REF_BIN, "-w", "0", "-q", "20", "-b", "20", "-f", d + "/ref.fa", d + "/s.bam", f"chr1:1-{ref_sample}"], stdout=fh, stderr=subprocess.DEVNULL)
