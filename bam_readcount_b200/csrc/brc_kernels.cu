@@ -940,8 +940,10 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
 //            (warp match + per-warp counts), so each group's events stay in file order;
 //   phase 2  thread = (site, library, statistic): walks its group's events in order and adds its one term to a register —
 //            the same sequence of float32 / double-rounded additions as the reference, so results stay bit-identical.
-//            The first passing base class is the primary allele (registers -> pstats); events of any other key (another
-//            base class, an indel allele) are handed, in order, to rare_event by the group's statistic-0 thread.
+//            The first passing base class is the primary allele (registers -> pstats).  The other base classes accumulate
+//            the same way in shared-memory cells (so a site whose first read carries a sequencing error costs the same),
+//            and become pool records at the end; indel alleles are handed, in order, to rare_event by the group's
+//            statistic-0 thread.
 // Integer statistics go through the same ordered loop: it keeps one code path and costs one predicated add.
 // ---------------------------------------------------------------------------------------------
 constexpr int DEEP_EVENTS = DEEP_THREADS * DEEP_MAX_SITES;
@@ -957,6 +959,8 @@ struct __align__(16) DeepSmem {
     uint32_t gcnt[DEEP_GROUPS + 1], gbase[DEEP_GROUPS + 1];
     uint32_t ncover[DEEP_GROUPS + 1], npass[DEEP_GROUPS + 1];
     int32_t first_libless[DEEP_MAX_SITES];        // -p: first covering read without a library (nothing after it counts)
+    int32_t recj[DEEP_GROUPS + 1];                // emit: pool record of the class being written
+    unsigned long long other[6][DEEP_THREADS];    // accumulators of the non-primary base classes, one cell per owner thread
 };
 
 template <bool PER_LIB>
@@ -974,6 +978,8 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
 
     for (int i = tid; i <= DEEP_GROUPS; i += DEEP_THREADS) { sm.ncover[i] = 0u; sm.npass[i] = 0u; }
     if (tid < DEEP_MAX_SITES) sm.first_libless[tid] = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) sm.other[c][tid] = 0ull;
 
     // phase-2 owner state
     const bool owner = tid < G * N_STATS;
@@ -983,29 +989,32 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
     uint32_t warn_nm = 0u, warn_sm = 0u;
     __syncthreads();
 
+    // the next block's descriptors and pool offsets are fetched while the current block is being accumulated
+    ReadDesc dn; uint64_t qoff_n = 0, soff_n = 0;
+    dn.pos = 0; dn.end = 0; dn.fm = 0u; dn.lib_nc = 0u;
+    if (lo + tid < hi) { dn = P.desc[lo + tid]; qoff_n = P.qual_off[lo + tid]; soff_n = P.seq_off[lo + tid]; }
+
     for (int32_t blk = lo; blk < hi; blk += DEEP_THREADS) {
         const int32_t r = blk + tid;
         const bool valid = r < hi;
+        const ReadDesc d = dn; const uint64_t qoff = qoff_n, soff = soff_n;
         // ---- phase 1a: coverage; -p: the first covering read without a library ----
-        int4 q0 = make_int4(0, 0, 0, 0);
-        if (valid) q0 = *reinterpret_cast<const int4 *>(&P.desc[r]);
-        const uint32_t fm = (uint32_t)q0.z, lib = (uint32_t)q0.w & 0xFFFFu;
+        const uint32_t fm = d.fm, lib = d.lib_nc & 0xFFFFu;
         bool cover[DEEP_MAX_SITES];
 #pragma unroll
         for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
             const int32_t site = ti.pos0 + sg;
-            cover[sg] = valid && sg < ti.n && site >= q0.x && site < q0.y;
+            cover[sg] = valid && sg < ti.n && site >= d.pos && site < d.end;
             if (PER_LIB && cover[sg] && lib == LIB_NONE) atomicMin(&sm.first_libless[sg], r);
         }
         for (int i = tid; i < DEEP_WARPS * (DEEP_GROUPS + 1); i += DEEP_THREADS) (&sm.wcnt[0][0])[i] = 0u;
         __syncthreads();
         // ---- phase 1b: the events of this read ----
         bool has[DEEP_MAX_SITES]; int grp[DEEP_MAX_SITES]; uint32_t w[DEEP_MAX_SITES][N_STATS];
-        uint32_t emeta[DEEP_MAX_SITES]; int eq[DEEP_MAX_SITES], ei[DEEP_MAX_SITES];
-        ReadDesc d; bool d_loaded = false;
+        uint32_t emeta[DEEP_MAX_SITES]; int eq[DEEP_MAX_SITES], ei[DEEP_MAX_SITES], gcov[DEEP_MAX_SITES];
 #pragma unroll
         for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
-            has[sg] = false; grp[sg] = 0; emeta[sg] = 0u; eq[sg] = 0; ei[sg] = 0;
+            has[sg] = false; grp[sg] = 0; emeta[sg] = 0u; eq[sg] = 0; ei[sg] = 0; gcov[sg] = -1;
             if (!cover[sg]) continue;
             uint32_t row = 0u;
             if (PER_LIB) {
@@ -1014,9 +1023,8 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
                 row = lib;
             }
             const int g = sg * n_rows + (int)row;
-            atomicAdd(&sm.ncover[g], 1u);
+            gcov[sg] = g;                                        // counts as a covering read of (site, row)
             const int32_t site = ti.pos0 + sg;
-            if (!d_loaded) { d = P.desc[r]; d_loaded = true; }
             int qpos, indel = 0;
             if (fm & FM_SIMPLE) qpos = site - d.pos + (int)d.cig;
             else {
@@ -1026,14 +1034,13 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
             }
             const uint32_t mapq = (fm >> 16) & 0xFFu;
             if ((int)mapq < P.min_mapq) continue;
-            const uint32_t bq = P.qual[P.qual_off[r] + (uint32_t)qpos];
+            const uint32_t bq = P.qual[qoff + (uint32_t)qpos];
+            const uint32_t byte = P.seq[soff + ((uint32_t)qpos >> 1)];      // both loads in flight before the filters
             if ((int)bq < P.min_bq) continue;
             if (fm & FLAG_FILTER) continue;
-            atomicAdd(&sm.npass[g], 1u);
             const bool base_part = !(indel > 0 && P.insertion_centric);
             const uint32_t nw = (indel != 0 ? 1u : 0u) + (base_part ? 1u : 0u);   // process_read calls that warn
             warn_nm += nw * ((fm >> 25) & 1u); warn_sm += nw * ((fm >> 26) & 1u);
-            const uint32_t byte = P.seq[P.seq_off[r] + ((uint32_t)qpos >> 1)];
             const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
             const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, d.rcp_l, d.rcp_clen);
             const uint32_t plus = (fm & 16u) ? 0u : 1u;
@@ -1051,7 +1058,10 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
         for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
             const unsigned m = __match_any_sync(0xffffffffu, has[sg] ? grp[sg] : -1 - lane);
             rank[sg] = __popc(m & ((1u << lane) - 1u));
-            if (has[sg] && rank[sg] == 0) sm.wcnt[warp][grp[sg]] = (uint32_t)__popc(m);
+            if (has[sg] && rank[sg] == 0) { sm.wcnt[warp][grp[sg]] = (uint32_t)__popc(m); atomicAdd(&sm.npass[grp[sg]], (uint32_t)__popc(m)); }
+            // covering reads of each (site, row), before the filters: one shared-memory atomic per group per warp
+            const unsigned mc = __match_any_sync(0xffffffffu, gcov[sg] >= 0 ? gcov[sg] : -1 - lane);
+            if (gcov[sg] >= 0 && (mc & ((1u << lane) - 1u)) == 0u) atomicAdd(&sm.ncover[gcov[sg]], (uint32_t)__popc(mc));
         }
         __syncthreads();
         if (warp == 0) {
@@ -1071,12 +1081,19 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
             sm.meta[slot] = emeta[sg]; sm.eread[slot] = r; sm.eqpos[slot] = eq[sg]; sm.eindel[slot] = ei[sg];
         }
         __syncthreads();
+        {   // prefetch the next block (lands while phase 2 runs)
+            const int32_t rn = r + DEEP_THREADS;
+            dn.pos = 0; dn.end = 0;
+            if (rn < hi) { dn = P.desc[rn]; qoff_n = P.qual_off[rn]; soff_n = P.seq_off[rn]; }
+        }
         // ---- phase 2: ordered accumulation ----
         if (owner) {
             const uint32_t b0 = sm.gbase[og], n = sm.gcnt[og];
+            uint32_t m_next = n ? sm.meta[b0] : 0u, x_next = n ? sm.term[oj][b0] : 0u;   // one event of look-ahead
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t slot = b0 + i;
-                const uint32_t m = sm.meta[slot];
+                const uint32_t m = m_next, x = x_next;
+                if (i + 1 < n) { m_next = sm.meta[slot + 1]; x_next = sm.term[oj][slot + 1]; }
                 if ((m & 8u) && oj == 0) {
                     const int indel = sm.eindel[slot];
                     sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
@@ -1085,18 +1102,42 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
                 const uint32_t base = m & 7u;
                 if (pbase == NO_BASE) pbase = base;
                 if (base == pbase) {
-                    const uint32_t x = sm.term[oj][slot];
                     if (oj == 6) acc_d = round_to_f32_precision(__dadd_rn(acc_d, __dsub_rn(1.0, (double)__uint_as_float(x))));
                     else if (oj == 7 || oj == 10 || oj == 12) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
                     else acc_u += x;
-                } else if (oj == 0) {
-                    sec_head = rare_event(P, sec_head, (int)base, 0, sm.eread[slot], sm.eqpos[slot], m >> 8, false);
+                } else {
+                    unsigned long long &cell = sm.other[base][tid];
+                    if (oj == 6) cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), __dsub_rn(1.0, (double)__uint_as_float(x)))));
+                    else if (oj == 7 || oj == 10 || oj == 12) cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x)));
+                    else cell = (unsigned long long)((uint32_t)cell + x);
                 }
             }
         }
         __syncthreads();
     }
 
+    // ---- emit: non-primary base classes become pool records (what site_emit does with its second class) ----
+    for (int c = 0; c < 6; ++c) {
+        const bool present = owner && (uint32_t)c != pbase && (uint32_t)sm.other[c][og * N_STATS] != 0u;   // stat 0 = read_count
+        if (present && oj == 0) {
+            const ResultsDev &R = P.res;
+            const int32_t j = atomicAdd(R.sec_count, 1);
+            if ((int64_t)j < R.sec_cap) {
+                R.sec_next[j] = sec_head; R.sec_kind[j] = (uint8_t)c; R.sec_len[j] = 0; R.sec_read[j] = 0; R.sec_qpos[j] = 0;
+                sec_head = j;
+            }
+            sm.recj[og] = j;
+        }
+        __syncthreads();
+        if (present) {
+            const int32_t j = sm.recj[og];
+            if ((int64_t)j < P.res.sec_cap) {
+                const unsigned long long cell = sm.other[c][tid];
+                P.res.sec_stats[(int64_t)oj * P.res.sec_cap + j] = oj == 6 ? __float_as_uint(__double2float_rn(__longlong_as_double((long long)cell))) : (uint32_t)cell;
+            }
+        }
+        __syncthreads();
+    }
     // ---- emit: the layout site_emit writes ----
     if (owner) {
         const ResultsDev &R = P.res;

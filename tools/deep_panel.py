@@ -17,7 +17,7 @@ t0 = time.time()
 batch, bounds = synth.synth_deep_panel(ref, sites, depth, seed=7, n_libs=8)
 print(f"generated {batch.n_reads} reads in {time.time()-t0:.1f}s")
 libs = [f"lib{i}" for i in range(8)]
-flags = dict(per_lib=True, max_cnt=100000000)
+flags = dict(per_lib=(len(sys.argv) <= 3 or sys.argv[3] != 'alllib'), max_cnt=100000000)
 eng = Engine(lib_names=libs, **flags)
 eng.set_reference(0, "chr1", L, ref.tobytes(), 0)
 t0 = time.time()
