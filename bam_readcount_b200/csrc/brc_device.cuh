@@ -153,7 +153,13 @@ struct PileupParams {
 constexpr int DEEP_MAX_SITES = 2;
 constexpr int DEEP_THREADS = 256;
 // one owner thread per (site, library row, statistic): the tile qualifies only if they fit one CTA
-__host__ __device__ inline bool deep_shape_ok(int n_sites, int n_rows) { return n_sites <= DEEP_MAX_SITES && n_sites * n_rows * N_STATS <= DEEP_THREADS; }
+// (integer, float and double statistics start on warp boundaries so a warp runs one kind of loop: 9G | 3G | G threads)
+__host__ __device__ inline int deep_flt_base(int G) { return (9 * G + 31) & ~31; }
+__host__ __device__ inline int deep_dbl_base(int G) { return (deep_flt_base(G) + 3 * G + 31) & ~31; }
+__host__ __device__ inline bool deep_shape_ok(int n_sites, int n_rows) {
+    const int G = n_sites * n_rows;
+    return n_sites <= DEEP_MAX_SITES && G >= 1 && deep_dbl_base(G) + G <= DEEP_THREADS;
+}
 
 struct PrecomputeParams {
     ReadsDev reads;

@@ -946,8 +946,11 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
 //            statistic-0 thread.
 // Integer statistics go through the same ordered loop: it keeps one code path and costs one predicated add.
 // ---------------------------------------------------------------------------------------------
+#ifdef BRC_DEEP_PROFILE
+__device__ unsigned long long g_deepprof[8];
+#endif
 constexpr int DEEP_EVENTS = DEEP_THREADS * DEEP_MAX_SITES;
-constexpr int DEEP_GROUPS = DEEP_THREADS / N_STATS;          // upper bound of n_sites * n_rows (deep_shape_ok)
+constexpr int DEEP_GROUPS = 17;                              // largest n_sites * n_rows deep_shape_ok admits
 constexpr int DEEP_WARPS = DEEP_THREADS / 32;
 struct __align__(16) DeepSmem {
     uint32_t term[N_STATS][DEEP_EVENTS + 1];   // +1: the 13 owners of a group read one column -> 13 different banks
@@ -981,11 +984,19 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
 #pragma unroll
     for (int c = 0; c < 6; ++c) sm.other[c][tid] = 0ull;
 
-    // phase-2 owner state
-    const bool owner = tid < G * N_STATS;
-    const int og = tid / N_STATS, oj = tid - og * N_STATS;   // group = site * n_rows + row
+    // phase-2 owner state: thread -> (statistic oj, group og = site * n_rows + row); kinds start on warp boundaries
+    bool owner = false; int og = 0, oj = 0, kind = 0;   // kind 0 integer, 1 float, 2 double-rounded
+    {
+        const int fb = deep_flt_base(G), db = deep_dbl_base(G);
+        if (tid < 9 * G) { const int k = tid / G; og = tid - k * G; oj = k < 6 ? k : (k == 6 ? 8 : (k == 7 ? 9 : 11)); kind = 0; owner = true; }
+        else if (tid >= fb && tid < fb + 3 * G) { const int k = (tid - fb) / G; og = tid - fb - k * G; oj = k == 0 ? 7 : (k == 1 ? 10 : 12); kind = 1; owner = true; }
+        else if (tid >= db && tid < db + G) { og = tid - db; oj = 6; kind = 2; owner = true; }
+    }
     uint32_t acc_u = 0u; float acc_f = 0.0f; double acc_d = 0.0;
     uint32_t pbase = NO_BASE; int32_t sec_head = -1;
+#ifdef BRC_DEEP_PROFILE
+    long long prof[6] = {0, 0, 0, 0, 0, 0};
+#endif
     uint32_t warn_nm = 0u, warn_sm = 0u;
     __syncthreads();
 
@@ -998,6 +1009,9 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
         const int32_t r = blk + tid;
         const bool valid = r < hi;
         const ReadDesc d = dn; const uint64_t qoff = qoff_n, soff = soff_n;
+#ifdef BRC_DEEP_PROFILE
+        const long long tq0 = clock64();
+#endif
         // ---- phase 1a: coverage; -p: the first covering read without a library ----
         const uint32_t fm = d.fm, lib = d.lib_nc & 0xFFFFu;
         bool cover[DEEP_MAX_SITES];
@@ -1009,6 +1023,9 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
         }
         for (int i = tid; i < DEEP_WARPS * (DEEP_GROUPS + 1); i += DEEP_THREADS) (&sm.wcnt[0][0])[i] = 0u;
         __syncthreads();
+#ifdef BRC_DEEP_PROFILE
+        const long long tq1 = clock64();
+#endif
         // ---- phase 1b: the events of this read ----
         bool has[DEEP_MAX_SITES]; int grp[DEEP_MAX_SITES]; uint32_t w[DEEP_MAX_SITES][N_STATS];
         uint32_t emeta[DEEP_MAX_SITES]; int eq[DEEP_MAX_SITES], ei[DEEP_MAX_SITES], gcov[DEEP_MAX_SITES];
@@ -1052,6 +1069,9 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
             emeta[sg] = base | (indel != 0 ? 8u : 0u) | (base_part ? 16u : 0u) | (bq << 8);
             eq[sg] = qpos; ei[sg] = indel; has[sg] = true; grp[sg] = g;
         }
+#ifdef BRC_DEEP_PROFILE
+        const long long tq2 = clock64();
+#endif
         // stable partition by group: rank inside the warp, then warp offsets, then group bases
         int rank[DEEP_MAX_SITES];
 #pragma unroll
@@ -1081,44 +1101,71 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
             sm.meta[slot] = emeta[sg]; sm.eread[slot] = r; sm.eqpos[slot] = eq[sg]; sm.eindel[slot] = ei[sg];
         }
         __syncthreads();
+#ifdef BRC_DEEP_PROFILE
+        const long long tq3 = clock64();
+        prof[0] += tq1 - tq0; prof[1] += tq2 - tq1; prof[2] += tq3 - tq2; prof[3] += 1;
+#endif
         {   // prefetch the next block (lands while phase 2 runs)
             const int32_t rn = r + DEEP_THREADS;
             dn.pos = 0; dn.end = 0;
             if (rn < hi) { dn = P.desc[rn]; qoff_n = P.qual_off[rn]; soff_n = P.seq_off[rn]; }
         }
-        // ---- phase 2: ordered accumulation ----
+        // ---- phase 2: ordered accumulation (one loop per kind of statistic; a warp holds one kind) ----
         if (owner) {
             const uint32_t b0 = sm.gbase[og], n = sm.gcnt[og];
-            uint32_t m_next = n ? sm.meta[b0] : 0u, x_next = n ? sm.term[oj][b0] : 0u;   // one event of look-ahead
-            for (uint32_t i = 0; i < n; ++i) {
-                const uint32_t slot = b0 + i;
-                const uint32_t m = m_next, x = x_next;
-                if (i + 1 < n) { m_next = sm.meta[slot + 1]; x_next = sm.term[oj][slot + 1]; }
-                if ((m & 8u) && oj == 0) {
-                    const int indel = sm.eindel[slot];
-                    sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
+            const uint32_t *mp = sm.meta + b0, *xp = sm.term[oj] + b0;
+            uint32_t m_next = n ? mp[0] : 0u, x_next = n ? xp[0] : 0u;   // one event of look-ahead
+            if (kind == 0) {
+                const bool is0 = oj == 0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t m = m_next, x = x_next;
+                    if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
+                    if (is0 && (m & 8u)) {
+                        const uint32_t slot = b0 + i;
+                        const int indel = sm.eindel[slot];
+                        sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
+                    }
+                    if (!(m & 16u)) continue;
+                    const uint32_t base = m & 7u;
+                    if (pbase == NO_BASE) pbase = base;
+                    if (base == pbase) acc_u += x;
+                    else { unsigned long long &cell = sm.other[base][tid]; cell = (unsigned long long)((uint32_t)cell + x); }
                 }
-                if (!(m & 16u)) continue;
-                const uint32_t base = m & 7u;
-                if (pbase == NO_BASE) pbase = base;
-                if (base == pbase) {
-                    if (oj == 6) acc_d = round_to_f32_precision(__dadd_rn(acc_d, __dsub_rn(1.0, (double)__uint_as_float(x))));
-                    else if (oj == 7 || oj == 10 || oj == 12) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
-                    else acc_u += x;
-                } else {
-                    unsigned long long &cell = sm.other[base][tid];
-                    if (oj == 6) cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), __dsub_rn(1.0, (double)__uint_as_float(x)))));
-                    else if (oj == 7 || oj == 10 || oj == 12) cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x)));
-                    else cell = (unsigned long long)((uint32_t)cell + x);
+            } else if (kind == 1) {
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t m = m_next, x = x_next;
+                    if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
+                    if (!(m & 16u)) continue;
+                    const uint32_t base = m & 7u;
+                    if (pbase == NO_BASE) pbase = base;
+                    if (base == pbase) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
+                    else { unsigned long long &cell = sm.other[base][tid]; cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x))); }
+                }
+            } else {
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t m = m_next, x = x_next;
+                    if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
+                    if (!(m & 16u)) continue;
+                    const uint32_t base = m & 7u;
+                    if (pbase == NO_BASE) pbase = base;
+                    const double t = __dsub_rn(1.0, (double)__uint_as_float(x));     // off the carried chain
+                    if (base == pbase) acc_d = round_to_f32_precision(__dadd_rn(acc_d, t));
+                    else { unsigned long long &cell = sm.other[base][tid]; cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), t))); }
                 }
             }
         }
+#ifdef BRC_DEEP_PROFILE
+        const long long tq4 = clock64();
+#endif
         __syncthreads();
+#ifdef BRC_DEEP_PROFILE
+        prof[4] += tq4 - tq3; prof[5] += clock64() - tq4;
+#endif
     }
 
     // ---- emit: non-primary base classes become pool records (what site_emit does with its second class) ----
     for (int c = 0; c < 6; ++c) {
-        const bool present = owner && (uint32_t)c != pbase && (uint32_t)sm.other[c][og * N_STATS] != 0u;   // stat 0 = read_count
+        const bool present = owner && (uint32_t)c != pbase && (uint32_t)sm.other[c][og] != 0u;   // thread og owns read_count of group og
         if (present && oj == 0) {
             const ResultsDev &R = P.res;
             const int32_t j = atomicAdd(R.sec_count, 1);
@@ -1133,7 +1180,7 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
             const int32_t j = sm.recj[og];
             if ((int64_t)j < P.res.sec_cap) {
                 const unsigned long long cell = sm.other[c][tid];
-                P.res.sec_stats[(int64_t)oj * P.res.sec_cap + j] = oj == 6 ? __float_as_uint(__double2float_rn(__longlong_as_double((long long)cell))) : (uint32_t)cell;
+                P.res.sec_stats[(int64_t)oj * P.res.sec_cap + j] = kind == 2 ? __float_as_uint(__double2float_rn(__longlong_as_double((long long)cell))) : (uint32_t)cell;
             }
         }
         __syncthreads();
@@ -1144,10 +1191,7 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
         const int sg = og / n_rows, row = og - sg * n_rows;
         const int64_t idx = (int64_t)row * R.n_slots + ti.slot0 + sg;
         const int64_t stride = (int64_t)R.n_rows * R.n_slots;
-        uint32_t v;
-        if (oj == 6) v = __float_as_uint(__double2float_rn(acc_d));
-        else if (oj == 7 || oj == 10 || oj == 12) v = __float_as_uint(acc_f);
-        else v = acc_u;
+        const uint32_t v = kind == 2 ? __float_as_uint(__double2float_rn(acc_d)) : (kind == 1 ? __float_as_uint(acc_f) : acc_u);
         R.pstats[(int64_t)oj * stride + idx] = v;
         if (oj == 0) {
             R.ncover[idx] = sm.ncover[og]; R.npass[idx] = sm.npass[og];
@@ -1160,7 +1204,19 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
         if (warn_sm) atomicAdd(P.res.warn + 0, (unsigned long long)warn_sm);
         if (warn_nm) atomicAdd(P.res.warn + 1, (unsigned long long)warn_nm);
     }
+#ifdef BRC_DEEP_PROFILE
+    if (tid == 0) for (int k = 0; k < 6; ++k) atomicAdd(&g_deepprof[k], (unsigned long long)prof[k]);
+#endif
 }
+
+#ifdef BRC_DEEP_PROFILE
+// cycles of thread 0 summed over CTAs: [0] phase 1a + barrier, [1] phase 1b, [2] partition + scatter, [3] blocks, [4] phase 2 (thread 0), [5] wait for the slowest owner
+extern "C" __attribute__((visibility("default"))) void brc_debug_deepprof(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_deepprof, sizeof(g_deepprof));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_deepprof, z, sizeof(z)); }
+}
+#endif
 
 cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s) {
     if (p.n_deep <= 0 || p.tile_count <= 0) return cudaSuccess;

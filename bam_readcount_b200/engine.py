@@ -17,6 +17,8 @@ from .batch import ReadBatch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbrc_engine.so")
+if os.environ.get("BRC_ENGINE_LIB"):        # debug hook: an instrumented build of the same library
+    LIB_PATH = os.environ["BRC_ENGINE_LIB"]
 
 N_STATS = 13
 KIND_INS, KIND_DEL, NO_BASE = 6, 7, 255

@@ -38,6 +38,12 @@ t_comp = time.time() - t0
 k0, k1 = eng.stage_ms(0), eng.stage_ms(1)
 ev = int(res.ncover.sum())
 print(f"push {t_push:.2f}s compute {t_comp:.2f}s  K0 {k0:.2f} ms  K1 {k1:.2f} ms  events {ev}  -> {ev/((k0+k1)/1e3):.3e} events/s (kernels), sites {n_sites}")
+if hasattr(eng.lib, "brc_debug_deepprof"):
+    import ctypes as C
+    out = (C.c_ulonglong * 8)()
+    eng.lib.brc_debug_deepprof(out, 1)
+    v = list(out); nb = max(1, v[3])
+    print("deep kernel, cycles per block of 256 reads (thread 0): phase1a+barrier %.0f  phase1b %.0f  partition+scatter %.0f  phase2(thread0) %.0f  wait-for-owners %.0f  blocks %d" % (v[0] / nb, v[1] / nb, v[2] / nb, v[4] / nb, v[5] / nb, v[3]))
 text = eng.format_text()
 # oracle on the first 2 and last site
 import cases
