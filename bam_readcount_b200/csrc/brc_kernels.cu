@@ -952,13 +952,19 @@ __device__ unsigned long long g_deepprof[8];
 constexpr int DEEP_EVENTS = DEEP_THREADS * DEEP_MAX_SITES;
 constexpr int DEEP_GROUPS = 17;                              // largest n_sites * n_rows deep_shape_ok admits
 constexpr int DEEP_WARPS = DEEP_THREADS / 32;
+struct __align__(16) DeepStage {                             // one block of reads, fetched with cp.async a block ahead
+    ReadDesc desc[DEEP_THREADS];
+    uint64_t qoff[DEEP_THREADS], soff[DEEP_THREADS];
+};
 struct __align__(16) DeepSmem {
-    uint32_t term[N_STATS][DEEP_EVENTS + 1];   // +1: the 13 owners of a group read one column -> 13 different banks
+    DeepStage stage[2];
+    uint32_t term[N_STATS][DEEP_EVENTS + 1];   // +1: the owners of a group read one column of different rows -> different banks
     uint32_t meta[DEEP_EVENTS];                // base class [0:3) | bit3 has indel | bit4 has base part | bq << 8
     int32_t eread[DEEP_EVENTS];                // read index
     int32_t eqpos[DEEP_EVENTS];
     int32_t eindel[DEEP_EVENTS];
     uint32_t wcnt[DEEP_WARPS][DEEP_GROUPS + 1];   // phase 1: events of group g in warp w -> exclusive offset inside the group
+    uint32_t gind[DEEP_GROUPS + 1];               // this block has an indel event in group g
     uint32_t gcnt[DEEP_GROUPS + 1], gbase[DEEP_GROUPS + 1];
     uint32_t ncover[DEEP_GROUPS + 1], npass[DEEP_GROUPS + 1];
     int32_t first_libless[DEEP_MAX_SITES];        // -p: first covering read without a library (nothing after it counts)
@@ -966,9 +972,32 @@ struct __align__(16) DeepSmem {
     unsigned long long other[6][DEEP_THREADS];    // accumulators of the non-primary base classes, one cell per owner thread
 };
 
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// this thread's read of the block starting at `blk` -> its own slots of stage st (no other thread touches them)
+__device__ __forceinline__ void deep_fetch(const PileupParams &P, DeepStage &st, int32_t r, int32_t hi, int tid) {
+    if (r < hi) {
+        const char *src = reinterpret_cast<const char *>(P.desc + r);
+        char *dst = reinterpret_cast<char *>(&st.desc[tid]);
+#pragma unroll
+        for (int k = 0; k < (int)sizeof(ReadDesc); k += 16) cp_async16(dst + k, src + k);
+        cp_async8(&st.qoff[tid], P.qual_off + r);
+        cp_async8(&st.soff[tid], P.seq_off + r);
+    }
+    cp_async_commit();
+}
+
 template <bool PER_LIB>
-__global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P) {
-    __shared__ DeepSmem sm;
+__global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams P) {
+    extern __shared__ __align__(128) uint8_t deep_smem_raw[];
+    DeepSmem &sm = *reinterpret_cast<DeepSmem *>(deep_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int32_t tile = P.deep_tiles[blockIdx.x];
     if (tile < P.tile_begin || tile >= P.tile_begin + P.tile_count) return;
@@ -979,6 +1008,7 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
     if (!deep_shape_ok(ti.n, n_rows) || hi - lo < P.deep_min_reads) return;   // pileup_kernel computes it (same predicate)
     const int G = ti.n * n_rows;
 
+    deep_fetch(P, sm.stage[0], lo + tid, hi, tid);
     for (int i = tid; i <= DEEP_GROUPS; i += DEEP_THREADS) { sm.ncover[i] = 0u; sm.npass[i] = 0u; }
     if (tid < DEEP_MAX_SITES) sm.first_libless[tid] = 0x7fffffff;
 #pragma unroll
@@ -994,24 +1024,24 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
     }
     uint32_t acc_u = 0u; float acc_f = 0.0f; double acc_d = 0.0;
     uint32_t pbase = NO_BASE; int32_t sec_head = -1;
+    uint32_t warn_nm = 0u, warn_sm = 0u;
 #ifdef BRC_DEEP_PROFILE
     long long prof[6] = {0, 0, 0, 0, 0, 0};
 #endif
-    uint32_t warn_nm = 0u, warn_sm = 0u;
     __syncthreads();
 
-    // the next block's descriptors and pool offsets are fetched while the current block is being accumulated
-    ReadDesc dn; uint64_t qoff_n = 0, soff_n = 0;
-    dn.pos = 0; dn.end = 0; dn.fm = 0u; dn.lib_nc = 0u;
-    if (lo + tid < hi) { dn = P.desc[lo + tid]; qoff_n = P.qual_off[lo + tid]; soff_n = P.seq_off[lo + tid]; }
-
-    for (int32_t blk = lo; blk < hi; blk += DEEP_THREADS) {
+    int stg = 0;
+    for (int32_t blk = lo; blk < hi; blk += DEEP_THREADS, stg ^= 1) {
         const int32_t r = blk + tid;
         const bool valid = r < hi;
-        const ReadDesc d = dn; const uint64_t qoff = qoff_n, soff = soff_n;
 #ifdef BRC_DEEP_PROFILE
         const long long tq0 = clock64();
 #endif
+        cp_async_wait_all();                                       // this thread's slots of stage[stg] have landed
+        ReadDesc d; uint64_t qoff = 0, soff = 0;
+        d.pos = 0; d.end = 0; d.fm = 0u; d.lib_nc = 0u;
+        if (valid) { d = sm.stage[stg].desc[tid]; qoff = sm.stage[stg].qoff[tid]; soff = sm.stage[stg].soff[tid]; }
+        deep_fetch(P, sm.stage[stg ^ 1], r + DEEP_THREADS, hi, tid);   // next block: in flight during this whole iteration
         // ---- phase 1a: coverage; -p: the first covering read without a library ----
         const uint32_t fm = d.fm, lib = d.lib_nc & 0xFFFFu;
         bool cover[DEEP_MAX_SITES];
@@ -1022,6 +1052,7 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
             if (PER_LIB && cover[sg] && lib == LIB_NONE) atomicMin(&sm.first_libless[sg], r);
         }
         for (int i = tid; i < DEEP_WARPS * (DEEP_GROUPS + 1); i += DEEP_THREADS) (&sm.wcnt[0][0])[i] = 0u;
+        if (tid <= DEEP_GROUPS) sm.gind[tid] = 0u;
         __syncthreads();
 #ifdef BRC_DEEP_PROFILE
         const long long tq1 = clock64();
@@ -1099,58 +1130,54 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
 #pragma unroll
             for (int k = 0; k < N_STATS; ++k) sm.term[k][slot] = w[sg][k];
             sm.meta[slot] = emeta[sg]; sm.eread[slot] = r; sm.eqpos[slot] = eq[sg]; sm.eindel[slot] = ei[sg];
+            if (ei[sg] != 0) sm.gind[grp[sg]] = 1u;
         }
         __syncthreads();
 #ifdef BRC_DEEP_PROFILE
         const long long tq3 = clock64();
         prof[0] += tq1 - tq0; prof[1] += tq2 - tq1; prof[2] += tq3 - tq2; prof[3] += 1;
 #endif
-        {   // prefetch the next block (lands while phase 2 runs)
-            const int32_t rn = r + DEEP_THREADS;
-            dn.pos = 0; dn.end = 0;
-            if (rn < hi) { dn = P.desc[rn]; qoff_n = P.qual_off[rn]; soff_n = P.seq_off[rn]; }
-        }
         // ---- phase 2: ordered accumulation (one loop per kind of statistic; a warp holds one kind) ----
         if (owner) {
             const uint32_t b0 = sm.gbase[og], n = sm.gcnt[og];
             const uint32_t *mp = sm.meta + b0, *xp = sm.term[oj] + b0;
-            uint32_t m_next = n ? mp[0] : 0u, x_next = n ? xp[0] : 0u;   // one event of look-ahead
-            if (kind == 0) {
-                const bool is0 = oj == 0;
+            // indel alleles: separate keys, so their (rare) events can be replayed first, in order, by the read_count owner
+            if (oj == 0 && sm.gind[og]) {
                 for (uint32_t i = 0; i < n; ++i) {
+                    const uint32_t m = mp[i];
+                    if (!(m & 8u)) continue;
+                    const uint32_t slot = b0 + i;
+                    const int indel = sm.eindel[slot];
+                    sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
+                }
+            }
+            uint32_t i = 0;
+            if (pbase == NO_BASE) {            // the first base event of the group fixes the primary class
+                for (; i < n; ++i) { const uint32_t m = mp[i]; if (m & 16u) { pbase = m & 7u; break; } }
+            }
+            const uint32_t want = 16u | pbase;  // (m & 0x17) == want  <=>  base event of the primary class
+            uint32_t m_next = i < n ? mp[i] : 0u, x_next = i < n ? xp[i] : 0u;   // one event of look-ahead
+            if (kind == 0) {
+                for (; i < n; ++i) {
                     const uint32_t m = m_next, x = x_next;
                     if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
-                    if (is0 && (m & 8u)) {
-                        const uint32_t slot = b0 + i;
-                        const int indel = sm.eindel[slot];
-                        sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
-                    }
-                    if (!(m & 16u)) continue;
-                    const uint32_t base = m & 7u;
-                    if (pbase == NO_BASE) pbase = base;
-                    if (base == pbase) acc_u += x;
-                    else { unsigned long long &cell = sm.other[base][tid]; cell = (unsigned long long)((uint32_t)cell + x); }
+                    if ((m & 0x17u) == want) acc_u += x;
+                    else if (m & 16u) { unsigned long long &cell = sm.other[m & 7u][tid]; cell = (unsigned long long)((uint32_t)cell + x); }
                 }
             } else if (kind == 1) {
-                for (uint32_t i = 0; i < n; ++i) {
+                for (; i < n; ++i) {
                     const uint32_t m = m_next, x = x_next;
                     if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
-                    if (!(m & 16u)) continue;
-                    const uint32_t base = m & 7u;
-                    if (pbase == NO_BASE) pbase = base;
-                    if (base == pbase) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
-                    else { unsigned long long &cell = sm.other[base][tid]; cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x))); }
+                    if ((m & 0x17u) == want) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
+                    else if (m & 16u) { unsigned long long &cell = sm.other[m & 7u][tid]; cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x))); }
                 }
             } else {
-                for (uint32_t i = 0; i < n; ++i) {
+                for (; i < n; ++i) {
                     const uint32_t m = m_next, x = x_next;
                     if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
-                    if (!(m & 16u)) continue;
-                    const uint32_t base = m & 7u;
-                    if (pbase == NO_BASE) pbase = base;
                     const double t = __dsub_rn(1.0, (double)__uint_as_float(x));     // off the carried chain
-                    if (base == pbase) acc_d = round_to_f32_precision(__dadd_rn(acc_d, t));
-                    else { unsigned long long &cell = sm.other[base][tid]; cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), t))); }
+                    if ((m & 0x17u) == want) acc_d = round_to_f32_precision(__dadd_rn(acc_d, t));
+                    else if (m & 16u) { unsigned long long &cell = sm.other[m & 7u][tid]; cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), t))); }
                 }
             }
         }
@@ -1162,6 +1189,7 @@ __global__ void __launch_bounds__(DEEP_THREADS) deep_site_kernel(PileupParams P)
         prof[4] += tq4 - tq3; prof[5] += clock64() - tq4;
 #endif
     }
+    cp_async_wait_all();
 
     // ---- emit: non-primary base classes become pool records (what site_emit does with its second class) ----
     for (int c = 0; c < 6; ++c) {
@@ -1220,8 +1248,17 @@ extern "C" __attribute__((visibility("default"))) void brc_debug_deepprof(unsign
 
 cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s) {
     if (p.n_deep <= 0 || p.tile_count <= 0) return cudaSuccess;
-    if (p.per_lib) deep_site_kernel<true><<<(unsigned)p.n_deep, DEEP_THREADS, 0, s>>>(p);
-    else deep_site_kernel<false><<<(unsigned)p.n_deep, DEEP_THREADS, 0, s>>>(p);
+    static bool attr_set[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e1 = cudaFuncSetAttribute(deep_site_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeepSmem));
+        cudaError_t e2 = cudaFuncSetAttribute(deep_site_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeepSmem));
+        if (e1 != cudaSuccess) return e1;
+        if (e2 != cudaSuccess) return e2;
+        attr_set[dev] = true;
+    }
+    if (p.per_lib) deep_site_kernel<true><<<(unsigned)p.n_deep, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);
+    else deep_site_kernel<false><<<(unsigned)p.n_deep, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);
     return cudaGetLastError();
 }
 
