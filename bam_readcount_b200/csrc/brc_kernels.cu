@@ -1057,12 +1057,12 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
 #ifdef BRC_DEEP_PROFILE
         const long long tq1 = clock64();
 #endif
-        // ---- phase 1b: the events of this read ----
-        bool has[DEEP_MAX_SITES]; int grp[DEEP_MAX_SITES]; uint32_t w[DEEP_MAX_SITES][N_STATS];
-        uint32_t emeta[DEEP_MAX_SITES]; int eq[DEEP_MAX_SITES], ei[DEEP_MAX_SITES], gcov[DEEP_MAX_SITES];
+        // ---- phase 1b: the events of this read.  Stage i: coverage / library / resolve_cigar2 for both sites ----
+        bool has[DEEP_MAX_SITES]; int grp[DEEP_MAX_SITES], eq[DEEP_MAX_SITES], ei[DEEP_MAX_SITES], gcov[DEEP_MAX_SITES];
+        const uint32_t mapq = (fm >> 16) & 0xFFu;
 #pragma unroll
         for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
-            has[sg] = false; grp[sg] = 0; emeta[sg] = 0u; eq[sg] = 0; ei[sg] = 0; gcov[sg] = -1;
+            has[sg] = false; grp[sg] = 0; eq[sg] = 0; ei[sg] = 0; gcov[sg] = -1;
             if (!cover[sg]) continue;
             uint32_t row = 0u;
             if (PER_LIB) {
@@ -1070,26 +1070,37 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
                 if (r > sm.first_libless[sg]) continue;          // pileup_func returned early at this site (R:...:281-284)
                 row = lib;
             }
-            const int g = sg * n_rows + (int)row;
-            gcov[sg] = g;                                        // counts as a covering read of (site, row)
+            grp[sg] = sg * n_rows + (int)row;
+            gcov[sg] = grp[sg];                                  // counts as a covering read of (site, row)
             const int32_t site = ti.pos0 + sg;
-            int qpos, indel = 0;
-            if (fm & FM_SIMPLE) qpos = site - d.pos + (int)d.cig;
+            if (fm & FM_SIMPLE) eq[sg] = site - d.pos + (int)d.cig;
             else {
                 const int3 rr = resolve_general(P.cigar + d.cig, d.n_cigar, d.pos, site);
                 if (rr.z) continue;
-                qpos = rr.x; indel = rr.y;
+                eq[sg] = rr.x; ei[sg] = rr.y;
             }
-            const uint32_t mapq = (fm >> 16) & 0xFFu;
-            if ((int)mapq < P.min_mapq) continue;
-            const uint32_t bq = P.qual[qoff + (uint32_t)qpos];
-            const uint32_t byte = P.seq[soff + ((uint32_t)qpos >> 1)];      // both loads in flight before the filters
-            if ((int)bq < P.min_bq) continue;
-            if (fm & FLAG_FILTER) continue;
+            has[sg] = (int)mapq >= P.min_mapq && !(fm & FLAG_FILTER);
+        }
+        // stage ii: the quality and base bytes of both sites, all loads in flight together
+        uint32_t bqv[DEEP_MAX_SITES], bytev[DEEP_MAX_SITES];
+#pragma unroll
+        for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
+            bqv[sg] = 0u; bytev[sg] = 0u;
+            if (has[sg]) { bqv[sg] = P.qual[qoff + (uint32_t)eq[sg]]; bytev[sg] = P.seq[soff + ((uint32_t)eq[sg] >> 1)]; }
+        }
+        // stage iii: base-quality filter, base class, the 13 terms
+        uint32_t w[DEEP_MAX_SITES][N_STATS], emeta[DEEP_MAX_SITES];
+#pragma unroll
+        for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
+            emeta[sg] = 0u;
+            if (!has[sg]) continue;
+            const uint32_t bq = bqv[sg];
+            if ((int)bq < P.min_bq) { has[sg] = false; continue; }
+            const int qpos = eq[sg], indel = ei[sg];
             const bool base_part = !(indel > 0 && P.insertion_centric);
             const uint32_t nw = (indel != 0 ? 1u : 0u) + (base_part ? 1u : 0u);   // process_read calls that warn
             warn_nm += nw * ((fm >> 25) & 1u); warn_sm += nw * ((fm >> 26) & 1u);
-            const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
+            const uint32_t base = canonical16((bytev[sg] >> ((~qpos & 1) << 2)) & 0xFu);
             const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, d.rcp_l, d.rcp_clen);
             const uint32_t plus = (fm & 16u) ? 0u : 1u;
             const bool has_q2 = d.q2 > -1;
@@ -1098,21 +1109,21 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
             w[sg][9] = has_q2 ? 1u : 0u; w[sg][10] = has_q2 ? __float_as_uint(t.q2term) : 0u;   // + 0.0f leaves the sum unchanged
             w[sg][11] = (uint32_t)d.clen; w[sg][12] = __float_as_uint(t.d3pterm);
             emeta[sg] = base | (indel != 0 ? 8u : 0u) | (base_part ? 16u : 0u) | (bq << 8);
-            eq[sg] = qpos; ei[sg] = indel; has[sg] = true; grp[sg] = g;
         }
 #ifdef BRC_DEEP_PROFILE
         const long long tq2 = clock64();
 #endif
-        // stable partition by group: rank inside the warp, then warp offsets, then group bases
+        // stable partition by group: one match per site on the covering reads' group; the passing events of a group are the
+        // matched lanes that also passed, so rank and count come from the same mask
         int rank[DEEP_MAX_SITES];
 #pragma unroll
         for (int sg = 0; sg < DEEP_MAX_SITES; ++sg) {
-            const unsigned m = __match_any_sync(0xffffffffu, has[sg] ? grp[sg] : -1 - lane);
-            rank[sg] = __popc(m & ((1u << lane) - 1u));
-            if (has[sg] && rank[sg] == 0) { sm.wcnt[warp][grp[sg]] = (uint32_t)__popc(m); atomicAdd(&sm.npass[grp[sg]], (uint32_t)__popc(m)); }
-            // covering reads of each (site, row), before the filters: one shared-memory atomic per group per warp
             const unsigned mc = __match_any_sync(0xffffffffu, gcov[sg] >= 0 ? gcov[sg] : -1 - lane);
-            if (gcov[sg] >= 0 && (mc & ((1u << lane) - 1u)) == 0u) atomicAdd(&sm.ncover[gcov[sg]], (uint32_t)__popc(mc));
+            const unsigned mp_ = mc & __ballot_sync(0xffffffffu, has[sg]);
+            const unsigned lt = (1u << lane) - 1u;
+            rank[sg] = __popc(mp_ & lt);
+            if (gcov[sg] >= 0 && (mc & lt) == 0u) atomicAdd(&sm.ncover[gcov[sg]], (uint32_t)__popc(mc));   // leader of the covering group
+            if (has[sg] && rank[sg] == 0) { sm.wcnt[warp][grp[sg]] = (uint32_t)__popc(mp_); atomicAdd(&sm.npass[grp[sg]], (uint32_t)__popc(mp_)); }
         }
         __syncthreads();
         if (warp == 0) {
@@ -1156,28 +1167,38 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
                 for (; i < n; ++i) { const uint32_t m = mp[i]; if (m & 16u) { pbase = m & 7u; break; } }
             }
             const uint32_t want = 16u | pbase;  // (m & 0x17) == want  <=>  base event of the primary class
-            uint32_t m_next = i < n ? mp[i] : 0u, x_next = i < n ? xp[i] : 0u;   // one event of look-ahead
+            // branch-free pass over the group's events: a non-primary event adds 0 (exact: the sums are non-negative) and
+            // raises `oth`; the rare non-primary events are then replayed, in order, into their shared-memory cells
+            uint32_t oth = 0u;
             if (kind == 0) {
-                for (; i < n; ++i) {
-                    const uint32_t m = m_next, x = x_next;
-                    if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
-                    if ((m & 0x17u) == want) acc_u += x;
-                    else if (m & 16u) { unsigned long long &cell = sm.other[m & 7u][tid]; cell = (unsigned long long)((uint32_t)cell + x); }
-                }
+                uint32_t a = acc_u;
+#pragma unroll 4
+                for (uint32_t k = i; k < n; ++k) { const uint32_t m = mp[k], x = xp[k]; const bool take = (m & 0x17u) == want; a += take ? x : 0u; oth |= take ? 0u : m; }
+                acc_u = a;
             } else if (kind == 1) {
-                for (; i < n; ++i) {
-                    const uint32_t m = m_next, x = x_next;
-                    if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
-                    if ((m & 0x17u) == want) acc_f = __fadd_rn(acc_f, __uint_as_float(x));
-                    else if (m & 16u) { unsigned long long &cell = sm.other[m & 7u][tid]; cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x))); }
-                }
+                float a = acc_f;
+#pragma unroll 4
+                for (uint32_t k = i; k < n; ++k) { const uint32_t m = mp[k], x = xp[k]; const bool take = (m & 0x17u) == want; a = __fadd_rn(a, take ? __uint_as_float(x) : 0.0f); oth |= take ? 0u : m; }
+                acc_f = a;
             } else {
-                for (; i < n; ++i) {
-                    const uint32_t m = m_next, x = x_next;
-                    if (i + 1 < n) { m_next = mp[i + 1]; x_next = xp[i + 1]; }
-                    const double t = __dsub_rn(1.0, (double)__uint_as_float(x));     // off the carried chain
-                    if ((m & 0x17u) == want) acc_d = round_to_f32_precision(__dadd_rn(acc_d, t));
-                    else if (m & 16u) { unsigned long long &cell = sm.other[m & 7u][tid]; cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), t))); }
+                double a = acc_d;
+#pragma unroll 2
+                for (uint32_t k = i; k < n; ++k) {
+                    const uint32_t m = mp[k], x = xp[k]; const bool take = (m & 0x17u) == want;
+                    const double t = take ? __dsub_rn(1.0, (double)__uint_as_float(x)) : 0.0;     // off the carried chain
+                    a = round_to_f32_precision(__dadd_rn(a, t)); oth |= take ? 0u : m;
+                }
+                acc_d = a;
+            }
+            if (oth & 16u) {
+                for (uint32_t k = i; k < n; ++k) {
+                    const uint32_t m = mp[k];
+                    if (!(m & 16u) || (m & 0x17u) == want) continue;
+                    const uint32_t x = xp[k];
+                    unsigned long long &cell = sm.other[m & 7u][tid];
+                    if (kind == 0) cell = (unsigned long long)((uint32_t)cell + x);
+                    else if (kind == 1) cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x)));
+                    else cell = (unsigned long long)__double_as_longlong(round_to_f32_precision(__dadd_rn(__longlong_as_double((long long)cell), __dsub_rn(1.0, (double)__uint_as_float(x)))));
                 }
             }
         }
