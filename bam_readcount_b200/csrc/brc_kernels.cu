@@ -946,6 +946,57 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
 //            statistic-0 thread.
 // Integer statistics go through the same ordered loop: it keeps one code path and costs one predicated add.
 // ---------------------------------------------------------------------------------------------
+// rare_event for deep_site_kernel: the same find-or-append and arithmetic, with the 13 accumulator loads issued together
+// (there one thread replays all indel events of a site, so the latency of 13 dependent read-modify-writes adds up)
+__device__ __noinline__ int32_t rare_event_deep(const PileupParams &P, int32_t head, int kind, int len, int32_t read, int qpos,
+                                           uint32_t bq, bool is_indel) {
+    const ResultsDev &S = P.res;
+    int32_t j = head;
+    while (j >= 0) {
+        if (S.sec_kind[j] == (uint8_t)kind && S.sec_len[j] == len) {
+            if (kind != KIND_INS) break;
+            // same inserted bases?  compare canonicalised read bases (R:bamreadcount.cpp:324-330)
+            const uint64_t oa = P.seq_off[read], ob = P.seq_off[S.sec_read[j]];
+            const int qb = S.sec_qpos[j];
+            bool same = true;
+            for (int k = 1; k <= len && same; ++k)
+                same = canonical16(seq_nib(P.seq, oa, qpos + k)) == canonical16(seq_nib(P.seq, ob, qb + k));
+            if (same) break;
+        }
+        j = S.sec_next[j];
+    }
+    if (j < 0) {
+        j = atomicAdd(S.sec_count, 1);
+        if ((int64_t)j >= S.sec_cap) return head;   // overflow: host sees sec_count > cap and retries with a larger pool
+        S.sec_next[j] = head; S.sec_kind[j] = (uint8_t)kind; S.sec_len[j] = len; S.sec_read[j] = read; S.sec_qpos[j] = qpos;
+#pragma unroll
+        for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = 0u;
+        head = j;
+    }
+    const ReadDesc d = P.desc[read];
+    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, 0.f, 0.f);
+    uint32_t *st = S.sec_stats + j;
+    const int64_t c = S.sec_cap;
+    uint32_t v[N_STATS];
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) v[k] = st[k * c];          // 13 independent loads in flight, then 13 stores
+    v[0] += 1u;
+    v[1] += (d.fm >> 16) & 0xFFu;
+    if (!is_indel) v[2] += bq;
+    v[3] += (uint32_t)d.se;
+    if (d.fm & 16u) v[5] += 1u; else v[4] += 1u;
+    v[6] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(v[6]), t.posterm)));
+    v[7] = __float_as_uint(__fadd_rn(__uint_as_float(v[7]), d.nmfrac));
+    v[8] += (uint32_t)d.mmq;
+    if (d.q2 > -1) { v[9] += 1u; v[10] = __float_as_uint(__fadd_rn(__uint_as_float(v[10]), t.q2term)); }
+    v[11] += (uint32_t)d.clen;
+    v[12] = __float_as_uint(__fadd_rn(__uint_as_float(v[12]), t.d3pterm));
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) st[k * c] = v[k];
+    return head;
+}
+
+
 #ifdef BRC_DEEP_PROFILE
 __device__ unsigned long long g_deepprof[8];
 #endif
@@ -1159,7 +1210,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
                     if (!(m & 8u)) continue;
                     const uint32_t slot = b0 + i;
                     const int indel = sm.eindel[slot];
-                    sec_head = rare_event(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
+                    sec_head = rare_event_deep(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
                 }
             }
             uint32_t i = 0;
