@@ -946,16 +946,15 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
 //            statistic-0 thread.
 // Integer statistics go through the same ordered loop: it keeps one code path and costs one predicated add.
 // ---------------------------------------------------------------------------------------------
-// rare_event for deep_site_kernel: the same find-or-append and arithmetic, with the 13 accumulator loads issued together
-// (there one thread replays all indel events of a site, so the latency of 13 dependent read-modify-writes adds up)
-__device__ __noinline__ int32_t rare_event_deep(const PileupParams &P, int32_t head, int kind, int len, int32_t read, int qpos,
-                                           uint32_t bq, bool is_indel) {
+// rare_event split in two for deep_site_kernel, where one thread replays every indel event of a (site, library):
+// find-or-append of the allele's record (a walk of dependent global loads — deep_site_kernel caches the result in shared
+// memory), and the accumulation with the 13 accumulator loads issued together.  Same arithmetic as rare_event.
+__device__ __noinline__ int32_t rare_find_or_append(const PileupParams &P, int32_t &head, int kind, int len, int32_t read, int qpos) {
     const ResultsDev &S = P.res;
     int32_t j = head;
     while (j >= 0) {
         if (S.sec_kind[j] == (uint8_t)kind && S.sec_len[j] == len) {
             if (kind != KIND_INS) break;
-            // same inserted bases?  compare canonicalised read bases (R:bamreadcount.cpp:324-330)
             const uint64_t oa = P.seq_off[read], ob = P.seq_off[S.sec_read[j]];
             const int qb = S.sec_qpos[j];
             bool same = true;
@@ -967,12 +966,16 @@ __device__ __noinline__ int32_t rare_event_deep(const PileupParams &P, int32_t h
     }
     if (j < 0) {
         j = atomicAdd(S.sec_count, 1);
-        if ((int64_t)j >= S.sec_cap) return head;   // overflow: host sees sec_count > cap and retries with a larger pool
+        if ((int64_t)j >= S.sec_cap) return j;   // overflow: host sees sec_count > cap and retries with a larger pool
         S.sec_next[j] = head; S.sec_kind[j] = (uint8_t)kind; S.sec_len[j] = len; S.sec_read[j] = read; S.sec_qpos[j] = qpos;
 #pragma unroll
         for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = 0u;
         head = j;
     }
+    return j;
+}
+__device__ __noinline__ void rare_accumulate(const PileupParams &P, int32_t j, int32_t read, int qpos, uint32_t bq, bool is_indel) {
+    const ResultsDev &S = P.res;
     const ReadDesc d = P.desc[read];
     const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, 0.f, 0.f);
     uint32_t *st = S.sec_stats + j;
@@ -993,9 +996,7 @@ __device__ __noinline__ int32_t rare_event_deep(const PileupParams &P, int32_t h
     v[12] = __float_as_uint(__fadd_rn(__uint_as_float(v[12]), t.d3pterm));
 #pragma unroll
     for (int k = 0; k < N_STATS; ++k) st[k * c] = v[k];
-    return head;
 }
-
 
 #ifdef BRC_DEEP_PROFILE
 __device__ unsigned long long g_deepprof[8];
@@ -1003,6 +1004,7 @@ __device__ unsigned long long g_deepprof[8];
 constexpr int DEEP_EVENTS = DEEP_THREADS * DEEP_MAX_SITES;
 constexpr int DEEP_GROUPS = 17;                              // largest n_sites * n_rows deep_shape_ok admits
 constexpr int DEEP_WARPS = DEEP_THREADS / 32;
+constexpr int DEEP_ICACHE = 8;
 struct __align__(16) DeepStage {                             // one block of reads, fetched with cp.async a block ahead
     ReadDesc desc[DEEP_THREADS];
     uint64_t qoff[DEEP_THREADS], soff[DEEP_THREADS];
@@ -1015,11 +1017,13 @@ struct __align__(16) DeepSmem {
     int32_t eqpos[DEEP_EVENTS];
     int32_t eindel[DEEP_EVENTS];
     uint32_t wcnt[DEEP_WARPS][DEEP_GROUPS + 1];   // phase 1: events of group g in warp w -> exclusive offset inside the group
-    uint32_t gind[DEEP_GROUPS + 1];               // this block has an indel event in group g
     uint32_t gcnt[DEEP_GROUPS + 1], gbase[DEEP_GROUPS + 1];
     uint32_t ncover[DEEP_GROUPS + 1], npass[DEEP_GROUPS + 1];
     int32_t first_libless[DEEP_MAX_SITES];        // -p: first covering read without a library (nothing after it counts)
     int32_t recj[DEEP_GROUPS + 1];                // emit: pool record of the class being written
+    uint32_t ikey[DEEP_GROUPS + 1][DEEP_ICACHE];  // indel alleles of a group already in the pool: packed (kind, length, inserted bases)
+    int32_t irec[DEEP_GROUPS + 1][DEEP_ICACHE];   //   -> pool record
+    uint32_t icount[DEEP_GROUPS + 1];
     unsigned long long other[6][DEEP_THREADS];    // accumulators of the non-primary base classes, one cell per owner thread
 };
 
@@ -1031,6 +1035,28 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// one indel event of a group (called by the group's read_count owner, in file order)
+__device__ __forceinline__ void deep_indel_event(const PileupParams &P, DeepSmem &sm, int og, int32_t &sec_head, int indel, int32_t read, int qpos, uint32_t bq) {
+    const int kind = indel > 0 ? KIND_INS : KIND_DEL, len = indel > 0 ? indel : -indel;
+    const bool cacheable = len <= 127 && (kind == KIND_DEL || len <= 8);
+    uint32_t key = 0u;
+    if (cacheable) {
+        key = (kind == KIND_INS ? 0x80000000u : 0u) | ((uint32_t)len << 24);
+        if (kind == KIND_INS) {
+            const uint64_t oa = P.seq_off[read];
+            for (int k = 1; k <= len; ++k) key |= canonical16(seq_nib(P.seq, oa, qpos + k)) << (3 * (k - 1));   // the allele string (R:...:324-330)
+        }
+    }
+    int32_t j = -1;
+    const uint32_t nc = sm.icount[og];
+    if (cacheable) for (uint32_t e = 0; e < nc; ++e) if (sm.ikey[og][e] == key) j = sm.irec[og][e];
+    if (j < 0) {
+        j = rare_find_or_append(P, sec_head, kind, len, read, qpos);
+        if (cacheable && (int64_t)j < P.res.sec_cap && nc < (uint32_t)DEEP_ICACHE) { sm.ikey[og][nc] = key; sm.irec[og][nc] = j; sm.icount[og] = nc + 1u; }
+    }
+    if ((int64_t)j < P.res.sec_cap) rare_accumulate(P, j, read, qpos, bq, true);
+}
 
 // this thread's read of the block starting at `blk` -> its own slots of stage st (no other thread touches them)
 __device__ __forceinline__ void deep_fetch(const PileupParams &P, DeepStage &st, int32_t r, int32_t hi, int tid) {
@@ -1060,7 +1086,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
     const int G = ti.n * n_rows;
 
     deep_fetch(P, sm.stage[0], lo + tid, hi, tid);
-    for (int i = tid; i <= DEEP_GROUPS; i += DEEP_THREADS) { sm.ncover[i] = 0u; sm.npass[i] = 0u; }
+    for (int i = tid; i <= DEEP_GROUPS; i += DEEP_THREADS) { sm.ncover[i] = 0u; sm.npass[i] = 0u; sm.icount[i] = 0u; }
     if (tid < DEEP_MAX_SITES) sm.first_libless[tid] = 0x7fffffff;
 #pragma unroll
     for (int c = 0; c < 6; ++c) sm.other[c][tid] = 0ull;
@@ -1103,7 +1129,6 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
             if (PER_LIB && cover[sg] && lib == LIB_NONE) atomicMin(&sm.first_libless[sg], r);
         }
         for (int i = tid; i < DEEP_WARPS * (DEEP_GROUPS + 1); i += DEEP_THREADS) (&sm.wcnt[0][0])[i] = 0u;
-        if (tid <= DEEP_GROUPS) sm.gind[tid] = 0u;
         __syncthreads();
 #ifdef BRC_DEEP_PROFILE
         const long long tq1 = clock64();
@@ -1192,7 +1217,6 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
 #pragma unroll
             for (int k = 0; k < N_STATS; ++k) sm.term[k][slot] = w[sg][k];
             sm.meta[slot] = emeta[sg]; sm.eread[slot] = r; sm.eqpos[slot] = eq[sg]; sm.eindel[slot] = ei[sg];
-            if (ei[sg] != 0) sm.gind[grp[sg]] = 1u;
         }
         __syncthreads();
 #ifdef BRC_DEEP_PROFILE
@@ -1203,49 +1227,49 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
         if (owner) {
             const uint32_t b0 = sm.gbase[og], n = sm.gcnt[og];
             const uint32_t *mp = sm.meta + b0, *xp = sm.term[oj] + b0;
-            // indel alleles: separate keys, so their (rare) events can be replayed first, in order, by the read_count owner
-            if (oj == 0 && sm.gind[og]) {
-                for (uint32_t i = 0; i < n; ++i) {
-                    const uint32_t m = mp[i];
-                    if (!(m & 8u)) continue;
-                    const uint32_t slot = b0 + i;
-                    const int indel = sm.eindel[slot];
-                    sec_head = rare_event_deep(P, sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, sm.eread[slot], sm.eqpos[slot], m >> 8, true);
-                }
-            }
             uint32_t i = 0;
             if (pbase == NO_BASE) {            // the first base event of the group fixes the primary class
                 for (; i < n; ++i) { const uint32_t m = mp[i]; if (m & 16u) { pbase = m & 7u; break; } }
             }
             const uint32_t want = 16u | pbase;  // (m & 0x17) == want  <=>  base event of the primary class
-            // branch-free pass over the group's events: a non-primary event adds 0 (exact: the sums are non-negative) and
-            // raises `oth`; the rare non-primary events are then replayed, in order, into their shared-memory cells
-            uint32_t oth = 0u;
-            if (kind == 0) {
-                uint32_t a = acc_u;
+            const bool is0 = oj == 0;
+            // indel-only events before the first base event (insertion-centric): still the read_count owner's to replay
+            if (is0) for (uint32_t k = 0; k < i; ++k) { const uint32_t m = mp[k]; if (m & 8u) deep_indel_event(P, sm, og, sec_head, sm.eindel[b0 + k], sm.eread[b0 + k], sm.eqpos[b0 + k], m >> 8); }
+            // 32 events at a time, branch-free: a non-primary event adds 0 (exact: the sums are non-negative) and sets a bit;
+            // the few marked events are then replayed in order — other base classes into their shared-memory cells, indel
+            // alleles (separate keys, so their order relative to base events is immaterial) into the record pool
+            for (uint32_t c0 = i; c0 < n; c0 += 32u) {
+                const uint32_t cn = min(32u, n - c0);
+                const uint32_t *mq = mp + c0, *xq = xp + c0;
+                uint32_t nm = 0u, im = 0u;
+                if (kind == 0) {
+                    uint32_t a = acc_u;
 #pragma unroll 4
-                for (uint32_t k = i; k < n; ++k) { const uint32_t m = mp[k], x = xp[k]; const bool take = (m & 0x17u) == want; a += take ? x : 0u; oth |= take ? 0u : m; }
-                acc_u = a;
-            } else if (kind == 1) {
-                float a = acc_f;
+                    for (uint32_t q = 0; q < cn; ++q) { const uint32_t m = mq[q], x = xq[q]; const bool take = (m & 0x17u) == want; a += take ? x : 0u; nm |= ((take ? 0u : m) >> 4 & 1u) << q; im |= (m >> 3 & 1u) << q; }
+                    acc_u = a;
+                } else if (kind == 1) {
+                    float a = acc_f;
 #pragma unroll 4
-                for (uint32_t k = i; k < n; ++k) { const uint32_t m = mp[k], x = xp[k]; const bool take = (m & 0x17u) == want; a = __fadd_rn(a, take ? __uint_as_float(x) : 0.0f); oth |= take ? 0u : m; }
-                acc_f = a;
-            } else {
-                double a = acc_d;
+                    for (uint32_t q = 0; q < cn; ++q) { const uint32_t m = mq[q], x = xq[q]; const bool take = (m & 0x17u) == want; a = __fadd_rn(a, take ? __uint_as_float(x) : 0.0f); nm |= ((take ? 0u : m) >> 4 & 1u) << q; }
+                    acc_f = a;
+                } else {
+                    double a = acc_d;
 #pragma unroll 2
-                for (uint32_t k = i; k < n; ++k) {
-                    const uint32_t m = mp[k], x = xp[k]; const bool take = (m & 0x17u) == want;
-                    const double t = take ? __dsub_rn(1.0, (double)__uint_as_float(x)) : 0.0;     // off the carried chain
-                    a = round_to_f32_precision(__dadd_rn(a, t)); oth |= take ? 0u : m;
+                    for (uint32_t q = 0; q < cn; ++q) {
+                        const uint32_t m = mq[q], x = xq[q]; const bool take = (m & 0x17u) == want;
+                        const double t = take ? __dsub_rn(1.0, (double)__uint_as_float(x)) : 0.0;     // off the carried chain
+                        a = round_to_f32_precision(__dadd_rn(a, t)); nm |= ((take ? 0u : m) >> 4 & 1u) << q;
+                    }
+                    acc_d = a;
                 }
-                acc_d = a;
-            }
-            if (oth & 16u) {
-                for (uint32_t k = i; k < n; ++k) {
-                    const uint32_t m = mp[k];
-                    if (!(m & 16u) || (m & 0x17u) == want) continue;
-                    const uint32_t x = xp[k];
+                if (is0) while (im) {
+                    const uint32_t q = (uint32_t)__ffs(im) - 1u; im &= im - 1u;
+                    const uint32_t slot = b0 + c0 + q;
+                    deep_indel_event(P, sm, og, sec_head, sm.eindel[slot], sm.eread[slot], sm.eqpos[slot], mq[q] >> 8);
+                }
+                while (nm) {
+                    const uint32_t q = (uint32_t)__ffs(nm) - 1u; nm &= nm - 1u;
+                    const uint32_t m = mq[q], x = xq[q];
                     unsigned long long &cell = sm.other[m & 7u][tid];
                     if (kind == 0) cell = (unsigned long long)((uint32_t)cell + x);
                     else if (kind == 1) cell = (unsigned long long)__float_as_uint(__fadd_rn(__uint_as_float((uint32_t)cell), __uint_as_float(x)));
