@@ -55,6 +55,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_profile_variant(define: str = "-DBRC_DEEP_PROFILE") -> str:
+    """An instrumented copy of the library (cycle counters inside a kernel) next to the product: libbrc_engine_prof.so.
+    Loaded by the tools with BRC_ENGINE_LIB=<path>; never by the tests or the bench."""
+    out = os.path.join(HERE, "libbrc_engine_prof.so")
+    cmd = [nvcc_path()] + NVCC_FLAGS + [define, "-I", os.path.join(HERE, "..", "include"), "-o", out] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout)
+        raise RuntimeError("nvcc failed building libbrc_engine_prof.so")
+    return out
+
+
 CLI = os.path.join(HERE, "brc-readcount")
 
 

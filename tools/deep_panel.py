@@ -1,5 +1,9 @@
 """Config-5 shape (ultra-deep panel): N single-base regions x DEPTH reads x 8 libraries, -p -d 100000000.
-Times the push path and the kernels, and checks a few sites bit-for-bit against the CPU oracle."""
+Times the push path and the kernels, and checks a few sites bit-for-bit against the CPU oracle.
+usage: deep_panel.py [n_sites] [depth] [alllib]
+  BRC_DEEP_MIN_READS=2147483647   pileup_kernel only (deep_site_kernel off)
+  BRC_ENGINE_LIB=bam_readcount_b200/libbrc_engine_prof.so   (python -c "from bam_readcount_b200 import build; build.build_profile_variant()")
+                                  prints deep_site_kernel's cycle profile per block of 256 reads"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
