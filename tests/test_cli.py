@@ -214,3 +214,43 @@ def test_cli_dense_site_list_matches_oracle(tmp_path):
             outs.append(p.stdout.decode("latin-1"))
         assert outs[0] == outs[1]
         assert outs[0] == want
+
+
+def test_cli_fetch_merging_two_contigs_unsorted_and_past_the_end(tmp_path):
+    """CPU: the merged fetch across contig changes, lines that go backwards, duplicates, a line past the contig's last read
+    and an unknown contig — record sets identical to the one-seek-per-line path and to the Python decoder."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    import dataclasses
+    from bam_readcount_b200 import synth
+    from bam_readcount_b200.batch import ReadBatch
+    exe = _cli()
+    a = cases.synthetic_case(L=30000, depth=20, seed=3, regions=((0, 1, 30000),), site_list=True)["batch"]
+    b = cases.synthetic_case(L=20000, depth=25, seed=4, regions=((0, 1, 20000),), site_list=True)["batch"]
+    b = dataclasses.replace(b, tid=np.ones_like(b.tid))
+    both = ReadBatch.concat([a, b])
+    d = str(tmp_path)
+    synth.write_sam(os.path.join(d, "s.sam"), both, [("chrA", 30000), ("chrB", 20000)])
+    subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-o", os.path.join(d, "s.bam"), os.path.join(d, "s.sam")])
+    subprocess.check_call([REF_SAMTOOLS, "index", os.path.join(d, "s.bam")])
+    lines = [("chrA", 100, 100), ("chrA", 101, 130), ("chrB", 5000, 5000), ("chrB", 5001, 5001), ("chrA", 120, 125), ("chrA", 120, 125),
+             ("chrB", 19990, 25000), ("chrA", 29999, 30000), ("chrZ", 5, 6), ("chrB", 1, 1), ("chrB", 2, 2), ("chrB", 3, 400)]
+    sl = tmp_path / "sites"
+    sl.write_text("".join(f"{c}\t{s}\t{e}\n" for c, s, e in lines))
+    outs = []
+    for extra in ({}, {"BRC_CLI_NO_MERGE": "1"}):
+        p = subprocess.run([exe, "-l", str(sl), os.path.join(d, "s.bam")], capture_output=True, env=dict(os.environ, BRC_CLI_DECODE_ONLY="1", **extra))
+        assert p.returncode == 0, p.stderr.decode()
+        outs.append(p.stdout.decode())
+        assert b"chrZ not found in bam file" in p.stderr
+    assert outs[0] == outs[1]
+    got = [tuple(int(x) for x in ln.split("\t")) for ln in outs[0].strip().splitlines()]
+    known = [ln for ln in lines if ln[0] != "chrZ"]
+    assert len(got) == len(known)
+    qo = both.qual_off.astype(np.int64)
+    for (c, s, e), g in zip(known, got):
+        tid = 0 if c == "chrA" else 1
+        idx = both.fetch(tid, max(s - 2, 0), e)
+        want = (tid, s - 1, e, len(idx), int(both.pos[idx].astype(np.int64).sum()), int(sum(int(both.qual[qo[i]:qo[i + 1]].astype(np.int64).sum()) for i in idx)))
+        assert g == want, (c, s, e)
