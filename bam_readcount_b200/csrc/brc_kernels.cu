@@ -1005,17 +1005,18 @@ constexpr int DEEP_EVENTS = DEEP_THREADS * DEEP_MAX_SITES;
 constexpr int DEEP_GROUPS = 17;                              // largest n_sites * n_rows deep_shape_ok admits
 constexpr int DEEP_WARPS = DEEP_THREADS / 32;
 constexpr int DEEP_ICACHE = 8;
+constexpr int DEEP_PAD = 136;                                // bank-skew slack of the event arrays: 0 + 1 + ... + 16 slots
 struct __align__(16) DeepStage {                             // one block of reads, fetched with cp.async a block ahead
     ReadDesc desc[DEEP_THREADS];
     uint64_t qoff[DEEP_THREADS], soff[DEEP_THREADS];
 };
 struct __align__(16) DeepSmem {
     DeepStage stage[2];
-    uint32_t term[N_STATS][DEEP_EVENTS + 1];   // +1: the owners of a group read one column of different rows -> different banks
-    uint32_t meta[DEEP_EVENTS];                // base class [0:3) | bit3 has indel | bit4 has base part | bq << 8
-    int32_t eread[DEEP_EVENTS];                // read index
-    int32_t eqpos[DEEP_EVENTS];
-    int32_t eindel[DEEP_EVENTS];
+    uint32_t term[N_STATS][DEEP_EVENTS + DEEP_PAD + 1];   // odd row length: the owners of a group read one column of different rows -> different banks
+    uint32_t meta[DEEP_EVENTS + DEEP_PAD];                // base class [0:3) | bit3 has indel | bit4 has base part | bq << 8
+    int32_t eread[DEEP_EVENTS + DEEP_PAD];                // read index
+    int32_t eqpos[DEEP_EVENTS + DEEP_PAD];
+    int32_t eindel[DEEP_EVENTS + DEEP_PAD];
     uint32_t wcnt[DEEP_WARPS][DEEP_GROUPS + 1];   // phase 1: events of group g in warp w -> exclusive offset inside the group
     uint32_t gcnt[DEEP_GROUPS + 1], gbase[DEEP_GROUPS + 1];
     uint32_t ncover[DEEP_GROUPS + 1], npass[DEEP_GROUPS + 1];
@@ -1205,9 +1206,20 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
         if (warp == 0) {
             uint32_t tot = 0u;
             if (lane < G) for (int wv = 0; wv < DEEP_WARPS; ++wv) { const uint32_t c = sm.wcnt[wv][lane]; sm.wcnt[wv][lane] = tot; tot += c; }
-            uint32_t incl = tot;
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            if (lane < G) { sm.gcnt[lane] = tot; sm.gbase[lane] = incl - tot; }
+            // group bases: consecutive segments, each start nudged (by < 32 slots) onto a bank no earlier group starts on.
+            // Owners of different groups read their i-th events together; equal-sized groups (a panel with evenly mixed
+            // libraries) would otherwise all start on multiples of 32 — a G-way conflict on every LDS of the ordered pass.
+            uint32_t cur = 0u, used = 0u, mybase = 0u;
+            for (int g = 0; g < G; ++g) {
+                const uint32_t tg = __shfl_sync(0xffffffffu, tot, g);
+                const uint32_t rot = cur & 31u;
+                const uint32_t taken = rot ? ((used >> rot) | (used << (32u - rot))) : used;   // bit p <=> bank (cur + p) % 32 is taken
+                const uint32_t base = cur + (uint32_t)__ffs((int)~taken) - 1u;                  // <= 17 groups: a free bank exists
+                used |= 1u << (base & 31u);
+                if (lane == g) mybase = base;
+                cur = base + tg;
+            }
+            if (lane < G) { sm.gcnt[lane] = tot; sm.gbase[lane] = mybase; }
         }
         __syncthreads();
 #pragma unroll
