@@ -1,5 +1,8 @@
 """Wide differential fuzz of the CPU oracle against the unmodified reference binary (needs oracle/_ref; CPU only).
-usage: fuzz_oracle_vs_reference.py [first_seed] [n_seeds]     (round 1: seeds 200..419, 1320 runs, 0 mismatches)"""
+usage: fuzz_oracle_vs_reference.py [first_seed] [n_seeds] [argv]
+  site-list mode (default): round 1, seeds 200..419: 1320 runs, 0 mismatches
+  argv: adjacent / overlapping command-line regions in arbitrary order (the never-cleared deletion queue): seeds 500..599,
+        600 runs, 0 mismatches"""
 import os, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -10,6 +13,7 @@ from bam_readcount_b200 import synth
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 220
+argv_mode = len(sys.argv) > 3 and sys.argv[3] == "argv"
 bad = n = 0
 t0 = time.time()
 for seed in range(first, first + count):
@@ -23,13 +27,18 @@ for seed in range(first, first + count):
     synth.write_sam(d + "/s.sam", case["batch"], [(name, L)], n_libs=len(case["lib_names"]))
     subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-o", d + "/s.bam", d + "/s.sam"])
     subprocess.check_call([REF_SAMTOOLS, "index", d + "/s.bam"])
-    regs = [(0, 1, L)] + [(0, int(a), int(a) + int(w)) for a, w in zip(rng.integers(1, L - 40, 6), rng.integers(0, 30, 6))]
+    if argv_mode:
+        a = int(rng.integers(20, L - 120)); b = int(rng.integers(1, L - 5))
+        regs = [(0, a, a + 30), (0, a + 31, a + 31), (0, a + 32, a + 60), (0, a + 50, a + 70), (0, b, b + 3), (0, a + 10, a + 12)]
+    else:
+        regs = [(0, 1, L)] + [(0, int(a), int(a) + int(w)) for a, w in zip(rng.integers(1, L - 40, 6), rng.integers(0, 30, 6))]
     case = dict(case, regions=regs)
     with open(d + "/sites", "w") as fh:
         fh.write("".join(f"{name}\t{b}\t{e}\n" for _, b, e in regs))
     for fname, fl in case["flag_sets"].items():
-        out, err, rc = run_reference_binary(["-w", "0", "-f", d + "/ref.fa"] + cases.flags_to_argv(fl) + ["-l", d + "/sites", d + "/s.bam"])
-        want, _, _ = cases.run_oracle(case, fl, site_list=True)
+        tail = [d + "/s.bam"] + [f"{name}:{b}-{e}" for _, b, e in regs] if argv_mode else ["-l", d + "/sites", d + "/s.bam"]
+        out, err, rc = run_reference_binary(["-w", "0", "-f", d + "/ref.fa"] + cases.flags_to_argv(fl) + tail)
+        want, _, _ = cases.run_oracle(case, fl, site_list=not argv_mode)
         n += 1
         if rc != 0 or want != out:
             bad += 1
