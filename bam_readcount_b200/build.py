@@ -68,6 +68,24 @@ def build_profile_variant(define: str = "-DBRC_DEEP_PROFILE") -> str:
     return out
 
 
+SYNTH_LIB = os.path.join(HERE, "libbrc_synth.so")
+
+
+def build_synth(force: bool = False) -> str:
+    """The counter-based workload generator (include/brc_synth.h): device kernels + the identical host implementation."""
+    src = os.path.join(CSRC, "brc_synth.cu")
+    hdr = os.path.join(HERE, "..", "include", "brc_synth.h")
+    if not force and os.path.exists(SYNTH_LIB) and os.path.getmtime(SYNTH_LIB) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return SYNTH_LIB
+    flags = [f for f in NVCC_FLAGS if f != "--fmad=false"]
+    cmd = [nvcc_path()] + flags + ["-I", os.path.join(HERE, "..", "include"), "-o", SYNTH_LIB, src]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout)
+        raise RuntimeError("nvcc failed building libbrc_synth.so")
+    return SYNTH_LIB
+
+
 CLI = os.path.join(HERE, "brc-readcount")
 
 
@@ -87,4 +105,5 @@ def build_cli(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_synth(force="--force" in sys.argv))
     print(build_cli(force="--force" in sys.argv))

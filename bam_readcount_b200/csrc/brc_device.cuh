@@ -107,24 +107,38 @@ struct ReadsDev {
     const uint8_t *qual;
 };
 
+// Packed per-site record (include/brc_engine.h "packed results"): 8 x u32 words per (row, slot), stored SoA as
+// words[w][row * n_slots + slot].  A site whose counters do not fit the narrow fields (depth > 255, 16-bit sums
+// overflowing) is ESCAPED: its words carry only the flags and its full-width record lives in the secondary pool.
+//   W0  ncover[0:8) | npass[8:16) | count[16:24) | plus[24:32)
+//   W1  pbase code [0:3) (0..5 = "=ACGTN", 6 = none, 7 = escaped) | libless flag bit 3 | has-secondary bit 4 |
+//       nq2 [8:16) | sum mapq [16:32)
+//   W2  sum baseq [0:16) | sum SE-mapq [16:32)
+//   W3  sum clipped length [0:16) | sum mismatch qualities [16:32)
+//   W4..W7  float32 bits: sum_event_location, sum_number_of_mismatches, sum_q2_distance, sum_3p_distance
+constexpr int N_WORDS = 8;
+constexpr uint32_t PB_NONE = 6u, PB_ESCAPE = 7u;
+constexpr uint32_t KIND_WIDE = 8u;    // secondary-pool record holding an escaped site's primary: kind = 8 + pbase code (0..6)
+
+// Secondary-pool record (72 B, AoS): other base classes, indel alleles and escaped primaries of one (row, slot).
+struct SecRec {
+    uint32_t slot;       // row * n_slots + slot
+    int32_t next;        // previous record of the same (row, slot) or -1 (device-internal chain)
+    uint32_t kind_len;   // kind [0:8) | length [8:32): indel length; escaped primary: ncover
+    int32_t read;        // representative read carrying the inserted bases; escaped primary: flags
+    int32_t qpos;        // its qpos; escaped primary: npass
+    uint32_t stats[N_STATS];
+};
+static_assert(sizeof(SecRec) == 72, "SecRec must be 72 bytes");
+
 struct ResultsDev {
     int32_t n_rows;
     int64_t n_slots;
-    uint32_t *ncover;     // [rows*slots]
-    uint32_t *npass;
-    uint8_t *flags;
-    uint8_t *pbase;
-    int32_t *sec_head;
-    uint32_t *pstats;     // [13][rows*slots]
+    uint32_t *words;      // [N_WORDS][rows*slots]
     // secondary key pool
     int64_t sec_cap;
     int32_t *sec_count;   // device counter (may exceed cap -> overflow)
-    int32_t *sec_next;
-    uint8_t *sec_kind;
-    int32_t *sec_len;
-    int64_t *sec_read;
-    int32_t *sec_qpos;
-    uint32_t *sec_stats;  // [13][sec_cap]
+    SecRec *sec;
     unsigned long long *warn; // [0]=SM missing events, [1]=NM missing events
 };
 

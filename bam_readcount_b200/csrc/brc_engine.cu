@@ -16,6 +16,9 @@
 
 using namespace brc;
 
+static_assert(sizeof(brc_sec_record) == sizeof(brc::SecRec), "public and device secondary records must match");
+static_assert(BRC_N_WORDS == brc::N_WORDS && BRC_KIND_WIDE == brc::KIND_WIDE && BRC_PB_ESCAPE == brc::PB_ESCAPE, "packed-format constants");
+
 namespace brc {
 int set_error(brc_engine *e, int status, const std::string &msg) { if (e) e->err = msg; return status; }
 int set_cuda_error(brc_engine *e, cudaError_t ce, const char *what) {
@@ -74,13 +77,11 @@ void brc_destroy(brc_engine *e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (auto &r : e->refs) r.dev.release();
-    DevBuf *bufs[] = {&e->d_refs, &e->d_desc, &e->d_tiles, &e->d_tile_lo, &e->d_tile_hi, &e->d_regions,
-                      &e->d_ncover, &e->d_npass, &e->d_flags, &e->d_pbase, &e->d_sec_head, &e->d_pstats, &e->d_sec_count,
-                      &e->d_sec_next, &e->d_sec_kind, &e->d_sec_len, &e->d_sec_read, &e->d_sec_qpos, &e->d_sec_stats, &e->d_warn};
+    DevBuf *bufs[] = {&e->d_refs, &e->d_desc, &e->d_tiles, &e->d_tile_lo, &e->d_tile_hi, &e->d_regions, &e->d_deep_tiles,
+                      &e->d_words, &e->d_sec, &e->d_sec_count, &e->d_warn};
     for (auto *b : bufs) b->release();
     for (auto &b : e->d_in) b.release();
-    PinBuf *pins[] = {&e->h_ncover, &e->h_npass, &e->h_flags, &e->h_pbase, &e->h_sec_head, &e->h_pstats, &e->h_sec_next,
-                      &e->h_sec_kind, &e->h_sec_len, &e->h_sec_read, &e->h_sec_qpos, &e->h_sec_stats, &e->h_misc};
+    PinBuf *pins[] = {&e->h_words, &e->h_sec, &e->h_misc};
     for (auto *b : pins) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->pipe_ev) if (ev) cudaEventDestroy(ev);
@@ -119,11 +120,37 @@ int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64
     return BRC_OK;
 }
 
+// Reference window already in DEVICE memory as ASCII (a generator or a device-side FASTA decoder wrote it): encoded on `stream`,
+// no host copy is kept — brc_format_* (deletion alleles, reference column) then needs brc_set_reference for that contig.
+int brc_set_reference_device(brc_engine *e, int32_t tid, const char *contig_name, int64_t chrom_len, int64_t win_beg,
+                             const char *dev_ascii, int64_t win_len, void *stream) {
+    if (!e || !dev_ascii || win_len < 0 || win_beg < 0 || chrom_len < 0) return BRC_E_INVALID;
+    cudaSetDevice(e->cfg.device);
+    cudaStream_t s = (cudaStream_t)stream;
+    HostRef *r = nullptr;
+    for (auto &x : e->refs) if (x.tid == tid) r = &x;
+    const bool is_new = r == nullptr;
+    if (!r) { e->refs.emplace_back(); r = &e->refs.back(); }
+    const void *old_ptr = r->dev.p;
+    r->tid = tid; r->name = contig_name ? contig_name : ""; r->chrom_len = chrom_len; r->win_beg = win_beg; r->win_len = win_len;
+    r->seq.clear();
+    CU(r->dev.reserve((size_t)win_len / 2 + 32), "cudaMalloc(reference)");
+    CU(cudaMemsetAsync(r->dev.p, 0xFF, (size_t)win_len / 2 + 32, s), "memset(reference)");
+    CU(launch_ref_encode(dev_ascii, r->dev.as<uint8_t>(), win_len, s), "reference encode");
+    (void)is_new; (void)old_ptr;
+    std::vector<RefWin> tab(e->refs.size());
+    for (size_t i = 0; i < e->refs.size(); ++i)
+        tab[i] = RefWin{e->refs[i].dev.as<char>(), e->refs[i].chrom_len, e->refs[i].win_beg, e->refs[i].win_len};
+    CU(e->d_refs.reserve(tab.size() * sizeof(RefWin)), "cudaMalloc(refs)");
+    CU(cudaMemcpyAsync(e->d_refs.p, tab.data(), tab.size() * sizeof(RefWin), cudaMemcpyHostToDevice, s), "H2D refs");   // pageable source: staged before the call returns
+    return BRC_OK;
+}
+
 int brc_reset(brc_engine *e) {
     if (!e) return BRC_E_INVALID;
     if (e->h2d_chunks) { cudaSetDevice(e->cfg.device); cudaStreamSynchronize(e->s_in); e->h2d_chunks = 0; }
     e->reads.clear(); e->is_borrowed = false; e->regions.clear(); e->region_open = false; e->adm.reset(); e->n_indel_ops = 0;
-    e->results_valid = false; e->planned = false; e->tiles.clear(); e->regions_dev.clear(); e->n_slots = 0;
+    e->results_valid = false; e->planned = false; e->tiles.clear(); e->regions_dev.clear(); e->n_slots = 0; e->wide.valid = false;
     for (auto &w : e->warn_counts) w = 0;
     return BRC_OK;
 }
@@ -357,12 +384,8 @@ static int alloc_outputs(brc_engine *e, int64_t n_reads_cap) {
     CU(e->d_tile_hi.reserve(nt * 4), "cudaMalloc(tile_hi)");
     CU(e->d_regions.reserve(std::max<size_t>(e->regions_dev.size(), 1) * sizeof(RegionDev)), "cudaMalloc(regions)");
     CU(e->d_deep_tiles.reserve(std::max<size_t>(e->deep_tiles.size(), 1) * 4), "cudaMalloc(deep_tiles)");
-    CU(e->d_ncover.reserve(rs1 * 4), "cudaMalloc(ncover)");
-    CU(e->d_npass.reserve(rs1 * 4), "cudaMalloc(npass)");
-    CU(e->d_flags.reserve(rs1), "cudaMalloc(flags)");
-    CU(e->d_pbase.reserve(rs1), "cudaMalloc(pbase)");
-    CU(e->d_sec_head.reserve(rs1 * 4), "cudaMalloc(sec_head)");
-    CU(e->d_pstats.reserve(rs1 * 4 * N_STATS), "cudaMalloc(pstats)");
+    if (rs >= 0xFFFFFFFFll) return set_error(e, BRC_E_INVALID, "more than 2^32 (library, site) slots in one batch: window the region");
+    CU(e->d_words.reserve(rs1 * 4 * N_WORDS), "cudaMalloc(words)");
     CU(e->d_sec_count.reserve(16), "cudaMalloc(sec_count)");
     CU(e->d_warn.reserve(32), "cudaMalloc(warn)");
     return BRC_OK;
@@ -371,23 +394,15 @@ static int alloc_outputs(brc_engine *e, int64_t n_reads_cap) {
 static int alloc_sec(brc_engine *e, int64_t cap) {
     cap = std::max<int64_t>(cap, 1024);
     e->sec_cap = cap;
-    CU(e->d_sec_next.reserve(cap * 4), "cudaMalloc(sec_next)");
-    CU(e->d_sec_kind.reserve(cap), "cudaMalloc(sec_kind)");
-    CU(e->d_sec_len.reserve(cap * 4), "cudaMalloc(sec_len)");
-    CU(e->d_sec_read.reserve(cap * 8), "cudaMalloc(sec_read)");
-    CU(e->d_sec_qpos.reserve(cap * 4), "cudaMalloc(sec_qpos)");
-    CU(e->d_sec_stats.reserve(cap * 4 * N_STATS), "cudaMalloc(sec_stats)");
+    CU(e->d_sec.reserve((size_t)cap * sizeof(SecRec)), "cudaMalloc(sec)");
     return BRC_OK;
 }
 
 static ResultsDev results_dev(brc_engine *e) {
     ResultsDev S{};
     S.n_rows = e->n_rows; S.n_slots = e->n_slots;
-    S.ncover = e->d_ncover.as<uint32_t>(); S.npass = e->d_npass.as<uint32_t>(); S.flags = e->d_flags.as<uint8_t>();
-    S.pbase = e->d_pbase.as<uint8_t>(); S.sec_head = e->d_sec_head.as<int32_t>(); S.pstats = e->d_pstats.as<uint32_t>();
-    S.sec_cap = e->sec_cap; S.sec_count = e->d_sec_count.as<int32_t>(); S.sec_next = e->d_sec_next.as<int32_t>();
-    S.sec_kind = e->d_sec_kind.as<uint8_t>(); S.sec_len = e->d_sec_len.as<int32_t>(); S.sec_read = e->d_sec_read.as<int64_t>();
-    S.sec_qpos = e->d_sec_qpos.as<int32_t>(); S.sec_stats = e->d_sec_stats.as<uint32_t>();
+    S.words = e->d_words.as<uint32_t>();
+    S.sec_cap = e->sec_cap; S.sec_count = e->d_sec_count.as<int32_t>(); S.sec = e->d_sec.as<SecRec>();
     S.warn = e->d_warn.as<unsigned long long>();
     return S;
 }
@@ -448,48 +463,77 @@ static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetch
     if ((int64_t)cnt > e->sec_cap) return set_error(e, BRC_E_OVERFLOW, "secondary key pool overflow (re-plan with a larger n_sec_cap)");
     e->h_n_sec = cnt;
     const int64_t rs1 = std::max<int64_t>(rs, 1), ns1 = std::max<int64_t>(cnt, 1);
-    CU(e->h_ncover.reserve(rs1 * 4), "pin"); CU(e->h_npass.reserve(rs1 * 4), "pin"); CU(e->h_flags.reserve(rs1), "pin");
-    CU(e->h_pbase.reserve(rs1), "pin"); CU(e->h_sec_head.reserve(rs1 * 4), "pin"); CU(e->h_pstats.reserve(rs1 * 4 * N_STATS), "pin");
-    CU(e->h_sec_next.reserve(ns1 * 4), "pin"); CU(e->h_sec_kind.reserve(ns1), "pin"); CU(e->h_sec_len.reserve(ns1 * 4), "pin");
-    CU(e->h_sec_read.reserve(ns1 * 8), "pin"); CU(e->h_sec_qpos.reserve(ns1 * 4), "pin"); CU(e->h_sec_stats.reserve(ns1 * 4 * N_STATS), "pin");
+    CU(e->h_words.reserve(rs1 * 4 * N_WORDS), "pin"); CU(e->h_sec.reserve((size_t)ns1 * sizeof(SecRec)), "pin");
     CU(e->h_misc.reserve(64), "pin");
-    if (rs && !slots_already_fetched) {
-        CU(cudaMemcpyAsync(e->h_ncover.p, e->d_ncover.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_npass.p, e->d_npass.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, rs, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_pbase.p, e->d_pbase.p, rs, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_sec_head.p, e->d_sec_head.p, rs * 4, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_pstats.p, e->d_pstats.p, rs * 4 * N_STATS, cudaMemcpyDeviceToHost, s), "D2H");
-    }
-    if (cnt) {
-        CU(cudaMemcpyAsync(e->h_sec_next.p, e->d_sec_next.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_sec_kind.p, e->d_sec_kind.p, (size_t)cnt, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_sec_len.p, e->d_sec_len.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_sec_read.p, e->d_sec_read.p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, s), "D2H");
-        CU(cudaMemcpyAsync(e->h_sec_qpos.p, e->d_sec_qpos.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H");
-        // compact the [13][sec_cap] device layout to [13][cnt] on the host
-        CU(cudaMemcpy2DAsync(e->h_sec_stats.p, (size_t)cnt * 4, e->d_sec_stats.p, (size_t)e->sec_cap * 4, (size_t)cnt * 4, N_STATS,
-                             cudaMemcpyDeviceToHost, s), "D2H");
-    }
-    e->h_sec_cap = cnt;
+    if (rs && !slots_already_fetched) CU(cudaMemcpyAsync(e->h_words.p, e->d_words.p, rs * 4 * N_WORDS, cudaMemcpyDeviceToHost, s), "D2H words");
+    if (cnt) CU(cudaMemcpyAsync(e->h_sec.p, e->d_sec.p, (size_t)cnt * sizeof(SecRec), cudaMemcpyDeviceToHost, s), "D2H sec");
     CU(cudaMemcpyAsync(e->h_misc.p, e->d_warn.p, 16, cudaMemcpyDeviceToHost, s), "D2H warn");
     CU(cudaStreamSynchronize(s), "sync D2H");
     const unsigned long long *w = e->h_misc.as<unsigned long long>();
     e->warn_counts[0] = (int64_t)w[0]; e->warn_counts[1] = (int64_t)w[1]; e->warn_counts[2] = 0;
-    // LIBRARY_UNAVAILABLE fires once per abandoned site callback (R:bamreadcount.cpp:281-284)
-    int64_t lu = 0;
-    if (e->cfg.per_lib) {
-        const uint8_t *fl = e->h_flags.as<uint8_t>();
-        for (int64_t sidx = 0; sidx < e->n_slots; ++sidx) {
-            bool ab = false;
-            for (int r = 0; r < e->n_rows && !ab; ++r) ab = (fl[(int64_t)r * e->n_slots + sidx] & 1) != 0;
-            lu += ab;
-        }
-    }
-    e->warn_counts[3] = lu;
-    e->results_valid = true; e->fmt_valid = false;
+    e->warn_counts[3] = -1;          // LIBRARY_UNAVAILABLE: counted from the flag bits on demand (brc_get_warning_counts)
+    e->results_valid = true; e->fmt_valid = false; e->wide.valid = false;
     return BRC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// packed host records -> the full-width arrays of brc_results (include/brc_engine.h)
+// ---------------------------------------------------------------------------------------------
+namespace brc {
+void ensure_wide(brc_engine *e) {
+    brc_engine::Wide &W = e->wide;
+    if (W.valid) return;
+    const int64_t rs = (int64_t)e->n_rows * e->n_slots, ns = e->h_n_sec;
+    const uint32_t *words = e->h_words.as<uint32_t>();
+    const SecRec *sec = e->h_sec.as<SecRec>();
+    W.ncover.resize((size_t)rs); W.npass.resize((size_t)rs); W.flags.resize((size_t)rs); W.pbase.resize((size_t)rs);
+    W.sec_head.resize((size_t)rs); W.pstats.resize((size_t)rs * N_STATS);
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)(hw ? hw : 1), (int64_t)16, rs / 262144 + 1}));
+    auto work = [&](int t) {
+        const int64_t lo = rs * t / nt, hi = rs * (t + 1) / nt;
+        uint32_t *ps = W.pstats.data();
+        for (int64_t i = lo; i < hi; ++i) {
+            const uint32_t w0 = words[i], w1 = words[rs + i], w2 = words[2 * rs + i], w3 = words[3 * rs + i];
+            const uint32_t count = (w0 >> 16) & 0xFFu, plus = w0 >> 24, pc = w1 & 7u;
+            W.ncover[(size_t)i] = w0 & 0xFFu; W.npass[(size_t)i] = (w0 >> 8) & 0xFFu;
+            W.flags[(size_t)i] = (uint8_t)((w1 >> 3) & 1u); W.pbase[(size_t)i] = (uint8_t)(pc < 6u ? pc : BRC_NO_BASE);
+            W.sec_head[(size_t)i] = -1;
+            ps[0 * rs + i] = count; ps[1 * rs + i] = w1 >> 16; ps[2 * rs + i] = w2 & 0xFFFFu; ps[3 * rs + i] = w2 >> 16;
+            ps[4 * rs + i] = plus; ps[5 * rs + i] = count - plus; ps[6 * rs + i] = words[4 * rs + i]; ps[7 * rs + i] = words[5 * rs + i];
+            ps[8 * rs + i] = w3 >> 16; ps[9 * rs + i] = (w1 >> 8) & 0xFFu; ps[10 * rs + i] = words[6 * rs + i]; ps[11 * rs + i] = w3 & 0xFFFFu;
+            ps[12 * rs + i] = words[7 * rs + i];
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    // secondary records: keys are chained per slot (order is immaterial to every consumer); escaped primaries fill their slot
+    const size_t n1 = (size_t)std::max<int64_t>(ns, 1);
+    W.sec_next.assign(n1, -1); W.sec_kind.assign(n1, 0); W.sec_len.assign(n1, 0); W.sec_read.assign(n1, 0); W.sec_qpos.assign(n1, 0);
+    W.sec_stats.assign(n1 * N_STATS, 0u);
+    for (int64_t j = 0; j < ns; ++j) {
+        const SecRec &r = sec[j];
+        const uint32_t kind = r.kind_len & 0xFFu, len = r.kind_len >> 8;
+        const int64_t i = (int64_t)r.slot;
+        if (i < 0 || i >= rs) continue;
+        if (kind >= KIND_WIDE) {
+            const uint32_t pc = kind - KIND_WIDE;
+            W.ncover[(size_t)i] = len; W.npass[(size_t)i] = (uint32_t)r.qpos; W.flags[(size_t)i] = (uint8_t)(r.read & 1);
+            W.pbase[(size_t)i] = (uint8_t)(pc < 6u ? pc : BRC_NO_BASE);
+            for (int k = 0; k < N_STATS; ++k) W.pstats[(size_t)((int64_t)k * rs + i)] = r.stats[k];
+            W.sec_kind[(size_t)j] = 0xFF;      // not a key
+            continue;
+        }
+        W.sec_kind[(size_t)j] = (uint8_t)kind; W.sec_len[(size_t)j] = (int32_t)len; W.sec_read[(size_t)j] = r.read; W.sec_qpos[(size_t)j] = r.qpos;
+        for (int k = 0; k < N_STATS; ++k) W.sec_stats[(size_t)((int64_t)k * (int64_t)n1 + j)] = r.stats[k];
+        W.sec_next[(size_t)j] = W.sec_head[(size_t)i]; W.sec_head[(size_t)i] = (int32_t)j;
+    }
+    W.n_sec = ns;
+    W.valid = true;
+}
+}  // namespace brc
 
 // Push path, one borrowed region: stream the batch through the GPU in read-index chunks so that the H2D copy of
 // chunk c+1, the kernels of chunk c and the D2H copy of the finished tiles of chunk c-1 overlap (PCIe is full
@@ -547,8 +591,7 @@ static int compute_pipelined(brc_engine *e) {
     R.seq = e->d_in[10].as<uint8_t>(); R.qual_off = e->d_in[11].as<uint64_t>(); R.qual = e->d_in[12].as<uint8_t>();
     // host result buffers
     const int64_t rs1 = std::max<int64_t>(rs, 1);
-    CU(e->h_ncover.reserve(rs1 * 4), "pin"); CU(e->h_npass.reserve(rs1 * 4), "pin"); CU(e->h_flags.reserve(rs1), "pin");
-    CU(e->h_pbase.reserve(rs1), "pin"); CU(e->h_sec_head.reserve(rs1 * 4), "pin"); CU(e->h_pstats.reserve(rs1 * 4 * N_STATS), "pin");
+    CU(e->h_words.reserve(rs1 * 4 * N_WORDS), "pin");
 
     PrecomputeParams P0; PileupParams P1;
     make_params(e, nullptr, P0, P1);
@@ -579,14 +622,10 @@ static int compute_pipelined(brc_engine *e) {
             const int64_t s0 = e->tiles[(size_t)tile_done].slot0;
             const int64_t s1 = tile_to < n_tiles ? e->tiles[(size_t)tile_to].slot0 : e->n_slots;
             const size_t w = (size_t)(s1 - s0);
-            const size_t pitch4 = (size_t)e->n_slots * 4, pitch1 = (size_t)e->n_slots;
+            const size_t pitch4 = (size_t)e->n_slots * 4;
             const int rows = e->n_rows;
-            CU(cudaMemcpy2DAsync((char *)e->h_ncover.p + s0 * 4, pitch4, (char *)e->d_ncover.p + s0 * 4, pitch4, w * 4, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
-            CU(cudaMemcpy2DAsync((char *)e->h_npass.p + s0 * 4, pitch4, (char *)e->d_npass.p + s0 * 4, pitch4, w * 4, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
-            CU(cudaMemcpy2DAsync((char *)e->h_flags.p + s0, pitch1, (char *)e->d_flags.p + s0, pitch1, w, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
-            CU(cudaMemcpy2DAsync((char *)e->h_pbase.p + s0, pitch1, (char *)e->d_pbase.p + s0, pitch1, w, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
-            CU(cudaMemcpy2DAsync((char *)e->h_sec_head.p + s0 * 4, pitch4, (char *)e->d_sec_head.p + s0 * 4, pitch4, w * 4, rows, cudaMemcpyDeviceToHost, e->s_out), "D2H");
-            CU(cudaMemcpy2DAsync((char *)e->h_pstats.p + s0 * 4, pitch4, (char *)e->d_pstats.p + s0 * 4, pitch4, w * 4, (size_t)rows * N_STATS, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            // the finished slots of all N_WORDS x rows word arrays: one strided copy
+            CU(cudaMemcpy2DAsync((char *)e->h_words.p + s0 * 4, pitch4, (char *)e->d_words.p + s0 * 4, pitch4, w * 4, (size_t)rows * N_WORDS, cudaMemcpyDeviceToHost, e->s_out), "D2H");
             tile_done = tile_to;
         }
     }
@@ -688,18 +727,41 @@ int brc_compute(brc_engine *e) {
 int brc_get_results(brc_engine *e, brc_results *out) {
     if (!e || !out) return BRC_E_INVALID;
     if (!e->results_valid) return set_error(e, BRC_E_INVALID, "get_results: no results (call brc_compute)");
+    brc::ensure_wide(e);
+    const brc_engine::Wide &W = e->wide;
     out->n_regions = (int64_t)e->regions.size(); out->regions = e->regions.data(); out->n_rows = e->n_rows; out->n_slots = e->n_slots;
-    out->ncover = e->h_ncover.as<uint32_t>(); out->npass = e->h_npass.as<uint32_t>(); out->flags = e->h_flags.as<uint8_t>();
-    out->pbase = e->h_pbase.as<uint8_t>(); out->sec_head = e->h_sec_head.as<int32_t>(); out->pstats = e->h_pstats.as<uint32_t>();
-    out->n_sec = e->h_n_sec; out->sec_next = e->h_sec_next.as<int32_t>(); out->sec_kind = e->h_sec_kind.as<uint8_t>();
-    out->sec_len = e->h_sec_len.as<int32_t>(); out->sec_read = e->h_sec_read.as<int64_t>(); out->sec_qpos = e->h_sec_qpos.as<int32_t>();
-    out->sec_stats = e->h_sec_stats.as<uint32_t>();
+    out->ncover = W.ncover.data(); out->npass = W.npass.data(); out->flags = W.flags.data();
+    out->pbase = W.pbase.data(); out->sec_head = W.sec_head.data(); out->pstats = W.pstats.data();
+    out->n_sec = W.n_sec; out->sec_next = W.sec_next.data(); out->sec_kind = W.sec_kind.data();
+    out->sec_len = W.sec_len.data(); out->sec_read = W.sec_read.data(); out->sec_qpos = W.sec_qpos.data();
+    out->sec_stats = W.sec_stats.data();
+    return BRC_OK;
+}
+
+int brc_get_packed_results(brc_engine *e, brc_packed_results *out) {
+    if (!e || !out) return BRC_E_INVALID;
+    if (!e->results_valid) return set_error(e, BRC_E_INVALID, "get_packed_results: no results (call brc_compute)");
+    out->n_regions = (int64_t)e->regions.size(); out->regions = e->regions.data(); out->n_rows = e->n_rows; out->n_slots = e->n_slots;
+    out->words = e->h_words.as<uint32_t>(); out->n_sec = e->h_n_sec; out->sec = e->h_sec.as<brc_sec_record>(); out->sec_count = nullptr;
     return BRC_OK;
 }
 
 int brc_get_warning_counts(brc_engine *e, int64_t out[4]) {
     if (!e || !out) return BRC_E_INVALID;
-    for (int k = 0; k < 4; ++k) out[k] = e->warn_counts[k];
+    if (e->results_valid && e->warn_counts[3] < 0) {
+        // LIBRARY_UNAVAILABLE fires once per abandoned site callback (R:bamreadcount.cpp:281-284)
+        int64_t lu = 0;
+        if (e->cfg.per_lib) {
+            const uint32_t *w1 = e->h_words.as<uint32_t>() + (int64_t)e->n_rows * e->n_slots;
+            for (int64_t sidx = 0; sidx < e->n_slots; ++sidx) {
+                bool ab = false;
+                for (int r = 0; r < e->n_rows && !ab; ++r) ab = (w1[(int64_t)r * e->n_slots + sidx] & 8u) != 0;
+                lu += ab;
+            }
+        }
+        e->warn_counts[3] = lu;
+    }
+    for (int k = 0; k < 4; ++k) out[k] = e->warn_counts[k] < 0 ? 0 : e->warn_counts[k];
     return BRC_OK;
 }
 
@@ -734,14 +796,11 @@ int brc_run_device(brc_engine *e, const brc_read_batch *b, const int32_t *dev_re
     return run_kernels(e, dev_region_of_read, (cudaStream_t)stream, false);
 }
 
-int brc_device_results(brc_engine *e, brc_results *out) {
+int brc_device_packed_results(brc_engine *e, brc_packed_results *out) {
     if (!e || !out || !e->planned) return BRC_E_INVALID;
     out->n_regions = (int64_t)e->regions.size(); out->regions = e->regions.data(); out->n_rows = e->n_rows; out->n_slots = e->n_slots;
-    out->ncover = e->d_ncover.as<uint32_t>(); out->npass = e->d_npass.as<uint32_t>(); out->flags = e->d_flags.as<uint8_t>();
-    out->pbase = e->d_pbase.as<uint8_t>(); out->sec_head = e->d_sec_head.as<int32_t>(); out->pstats = e->d_pstats.as<uint32_t>();
-    out->n_sec = e->sec_cap; out->sec_next = e->d_sec_next.as<int32_t>(); out->sec_kind = e->d_sec_kind.as<uint8_t>();
-    out->sec_len = e->d_sec_len.as<int32_t>(); out->sec_read = e->d_sec_read.as<int64_t>(); out->sec_qpos = e->d_sec_qpos.as<int32_t>();
-    out->sec_stats = e->d_sec_stats.as<uint32_t>();
+    out->words = e->d_words.as<uint32_t>(); out->n_sec = e->sec_cap; out->sec = e->d_sec.as<brc_sec_record>();
+    out->sec_count = e->d_sec_count.as<int32_t>();
     return BRC_OK;
 }
 

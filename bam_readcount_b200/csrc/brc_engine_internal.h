@@ -110,16 +110,23 @@ struct brc_engine {
     // device buffers
     brc::DevBuf d_in[14];            // uploaded read arrays (push path)
     brc::DevBuf d_desc, d_tiles, d_tile_lo, d_tile_hi, d_regions, d_deep_tiles;
-    brc::DevBuf d_ncover, d_npass, d_flags, d_pbase, d_sec_head, d_pstats;
-    brc::DevBuf d_sec_count, d_sec_next, d_sec_kind, d_sec_len, d_sec_read, d_sec_qpos, d_sec_stats, d_warn;
+    brc::DevBuf d_words;             // packed per-site records [N_WORDS][rows*slots]
+    brc::DevBuf d_sec, d_sec_count, d_warn;   // secondary pool (SecRec[sec_cap]) + its counter
     brc::ReadsDev dev_reads{};       // what the kernels read (push path: d_in; device path: caller's pointers)
 
-    // host results (pinned)
-    brc::PinBuf h_ncover, h_npass, h_flags, h_pbase, h_sec_head, h_pstats;
-    brc::PinBuf h_sec_next, h_sec_kind, h_sec_len, h_sec_read, h_sec_qpos, h_sec_stats, h_misc;
+    // host results: the PACKED records as they come off the device (pinned) ...
+    brc::PinBuf h_words, h_sec, h_misc;
     int64_t h_n_sec = 0;
-    int64_t h_sec_cap = 0;           // stride of h_sec_stats
     bool results_valid = false;
+    // ... and the full-width view brc_get_results / the text emitter read, expanded from them on first use (ensure_wide)
+    struct Wide {
+        std::vector<uint32_t> ncover, npass, pstats, sec_stats;
+        std::vector<uint8_t> flags, pbase, sec_kind;
+        std::vector<int32_t> sec_head, sec_next, sec_len, sec_qpos;
+        std::vector<int64_t> sec_read;
+        int64_t n_sec = 0;           // records that are keys (escaped primaries are folded into the slot arrays)
+        bool valid = false;
+    } wide;
     int64_t warn_counts[4] = {0, 0, 0, 0};
 
     // text of the last brc_format_* call, so the usual size-query + fill pair formats only once
@@ -132,4 +139,5 @@ namespace brc {
 int set_error(brc_engine *e, int status, const std::string &msg);
 int set_cuda_error(brc_engine *e, cudaError_t ce, const char *what);
 const HostRef *find_ref(const brc_engine *e, int32_t tid);
+void ensure_wide(brc_engine *e);   // expand the packed host records into e->wide (multi-threaded; no-op when already done)
 }  // namespace brc

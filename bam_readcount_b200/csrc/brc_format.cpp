@@ -71,11 +71,12 @@ struct View {   // raw result arrays of one engine
     const int32_t *shead, *snext, *slen, *sqpos; const int64_t *sread;
     const uint8_t *h_seq; const uint64_t *h_seq_off;
     View(const brc_engine *en, int64_t g) : e(en), rg(&en->regions[(size_t)g]), ref(brc::find_ref(en, rg->tid)) {
-        rows = e->n_rows; NS = e->n_slots; RS = (int64_t)rows * NS; SC = e->h_sec_cap;
-        ncover = e->h_ncover.as<uint32_t>(); npass = e->h_npass.as<uint32_t>(); pstats = e->h_pstats.as<uint32_t>(); sstats = e->h_sec_stats.as<uint32_t>();
-        flags = e->h_flags.as<uint8_t>(); pbase = e->h_pbase.as<uint8_t>(); skind = e->h_sec_kind.as<uint8_t>();
-        shead = e->h_sec_head.as<int32_t>(); snext = e->h_sec_next.as<int32_t>(); slen = e->h_sec_len.as<int32_t>(); sqpos = e->h_sec_qpos.as<int32_t>();
-        sread = e->h_sec_read.as<int64_t>(); h_seq = e->host_seq(); h_seq_off = e->host_seq_off();
+        const brc_engine::Wide &W = e->wide;            // full-width view of the packed device records (brc::ensure_wide)
+        rows = e->n_rows; NS = e->n_slots; RS = (int64_t)rows * NS; SC = (int64_t)W.sec_next.size();
+        ncover = W.ncover.data(); npass = W.npass.data(); pstats = W.pstats.data(); sstats = W.sec_stats.data();
+        flags = W.flags.data(); pbase = W.pbase.data(); skind = W.sec_kind.data();
+        shead = W.sec_head.data(); snext = W.sec_next.data(); slen = W.sec_len.data(); sqpos = W.sec_qpos.data();
+        sread = W.sec_read.data(); h_seq = e->host_seq(); h_seq_off = e->host_seq_off();
     }
 };
 
@@ -112,7 +113,7 @@ void format_site(const View &V, int32_t s, const char *const *lib_names, EmitSta
                 in.allele = "-";
                 for (int k = 1; k <= V.slen[j]; ++k) {
                     int64_t p = pos + k; char c = 'N';
-                    if (V.ref && p >= V.ref->win_beg && p < V.ref->win_beg + V.ref->win_len && p < V.ref->chrom_len) c = V.ref->seq[(size_t)(p - V.ref->win_beg)];
+                    if (V.ref && p >= V.ref->win_beg && p < V.ref->win_beg + (int64_t)V.ref->seq.size() && p < V.ref->chrom_len) c = V.ref->seq[(size_t)(p - V.ref->win_beg)];
                     in.allele += c;
                 }
             }
@@ -137,7 +138,7 @@ void format_site(const View &V, int32_t s, const char *const *lib_names, EmitSta
     }
     if (emit && pos >= rg.beg && pos < rg.end) {
         char rb = 'N';
-        if (V.ref && pos < V.ref->chrom_len && pos >= V.ref->win_beg && pos < V.ref->win_beg + V.ref->win_len) rb = V.ref->seq[(size_t)(pos - V.ref->win_beg)];
+        if (V.ref && pos < V.ref->chrom_len && pos >= V.ref->win_beg && pos < V.ref->win_beg + (int64_t)V.ref->seq.size()) rb = V.ref->seq[(size_t)(pos - V.ref->win_beg)];   // a device-only reference window (brc_set_reference_device) has no characters here
         if (V.ref) out += V.ref->name; else out += '?';
         out += '\t'; put_u(out, (uint64_t)(pos + 1)); out += '\t'; out += rb; out += '\t';
         put_u(out, (uint64_t)((int64_t)mapq_n + extra_depth));
@@ -229,6 +230,7 @@ bool format_many_site_list_regions(const brc_engine *e, const char *const *lib_n
 // the caller's usual pattern is a size query (buf == NULL) followed by the fill: format once, keep the parts
 void ensure_formatted(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const char *const *lib_names) {
     if (e->fmt_valid && e->fmt_key[0] == k0 && e->fmt_key[1] == k1 && e->fmt_key[2] == k2) return;
+    brc::ensure_wide(e);
     e->fmt_parts.clear();
     EmitState st(e->n_rows);
     if (k1 == -1) {   // whole regions

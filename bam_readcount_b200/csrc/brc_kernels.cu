@@ -540,46 +540,63 @@ __device__ __noinline__ int3 resolve_general(const uint32_t *cig, uint32_t n_cig
 // Rare keys (indel alleles, a third base class at a site): find-or-append a record in the thread's private
 // chain in the L2-resident pool and accumulate there.  Recomputes the event from the global descriptor so
 // the hot loop carries no state for it.  Returns the new chain head.
-__device__ __noinline__ int32_t rare_event(const PileupParams &P, int32_t head, int kind, int len, int32_t read, int qpos,
-                                           uint32_t bq, bool is_indel) {
+__device__ __forceinline__ bool same_insertion(const PileupParams &P, int32_t read_a, int qpos_a, int32_t read_b, int qpos_b, int len) {
+    // same inserted bases?  compare canonicalised read bases (R:bamreadcount.cpp:324-330)
+    const uint64_t oa = P.seq_off[read_a], ob = P.seq_off[read_b];
+    bool same = true;
+    for (int k = 1; k <= len && same; ++k)
+        same = canonical16(seq_nib(P.seq, oa, qpos_a + k)) == canonical16(seq_nib(P.seq, ob, qpos_b + k));
+    return same;
+}
+__device__ __forceinline__ void sec_init(SecRec &r, uint32_t slot, int32_t next, uint32_t kind, uint32_t len, int32_t read, int32_t qpos) {
+    r.slot = slot; r.next = next; r.kind_len = kind | (len << 8); r.read = read; r.qpos = qpos;
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) r.stats[k] = 0u;
+}
+// one event of BasicStat::process_read into a pool record (slow, exact IEEE path)
+__device__ __forceinline__ void sec_accumulate(const PileupParams &P, SecRec &r, int32_t read, int qpos, uint32_t bq, bool is_indel) {
+    const ReadDesc d = P.desc[read];
+    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, 0.f, 0.f);
+    uint32_t v[N_STATS];
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) v[k] = r.stats[k];
+    v[0] += 1u;
+    v[1] += (d.fm >> 16) & 0xFFu;
+    if (!is_indel) v[2] += bq;
+    v[3] += (uint32_t)d.se;
+    if (d.fm & 16u) v[5] += 1u; else v[4] += 1u;
+    v[6] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(v[6]), t.posterm)));
+    v[7] = __float_as_uint(__fadd_rn(__uint_as_float(v[7]), d.nmfrac));
+    v[8] += (uint32_t)d.mmq;
+    if (d.q2 > -1) { v[9] += 1u; v[10] = __float_as_uint(__fadd_rn(__uint_as_float(v[10]), t.q2term)); }
+    v[11] += (uint32_t)d.clen;
+    v[12] = __float_as_uint(__fadd_rn(__uint_as_float(v[12]), t.d3pterm));
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) r.stats[k] = v[k];
+}
+// find-or-append of the allele's record in the chain starting at `head`; returns the record index (>= sec_cap on overflow:
+// the host sees sec_count > cap and retries with a larger pool)
+__device__ __noinline__ int32_t rare_find_or_append(const PileupParams &P, int32_t &head, uint32_t slot, int kind, int len, int32_t read, int qpos) {
     const ResultsDev &S = P.res;
+    const uint32_t want = (uint32_t)kind | ((uint32_t)len << 8);
     int32_t j = head;
     while (j >= 0) {
-        if (S.sec_kind[j] == (uint8_t)kind && S.sec_len[j] == len) {
-            if (kind != KIND_INS) break;
-            // same inserted bases?  compare canonicalised read bases (R:bamreadcount.cpp:324-330)
-            const uint64_t oa = P.seq_off[read], ob = P.seq_off[S.sec_read[j]];
-            const int qb = S.sec_qpos[j];
-            bool same = true;
-            for (int k = 1; k <= len && same; ++k)
-                same = canonical16(seq_nib(P.seq, oa, qpos + k)) == canonical16(seq_nib(P.seq, ob, qb + k));
-            if (same) break;
-        }
-        j = S.sec_next[j];
+        const SecRec &r = S.sec[j];
+        if (r.kind_len == want && (kind != KIND_INS || same_insertion(P, read, qpos, r.read, r.qpos, len))) break;
+        j = r.next;
     }
     if (j < 0) {
         j = atomicAdd(S.sec_count, 1);
-        if ((int64_t)j >= S.sec_cap) return head;   // overflow: host sees sec_count > cap and retries with a larger pool
-        S.sec_next[j] = head; S.sec_kind[j] = (uint8_t)kind; S.sec_len[j] = len; S.sec_read[j] = read; S.sec_qpos[j] = qpos;
-#pragma unroll
-        for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = 0u;
+        if ((int64_t)j >= S.sec_cap) return j;
+        sec_init(S.sec[j], slot, head, (uint32_t)kind, (uint32_t)len, read, qpos);
         head = j;
     }
-    const ReadDesc d = P.desc[read];
-    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, 0.f, 0.f);
-    uint32_t *st = S.sec_stats + j;
-    const int64_t c = S.sec_cap;
-    st[0 * c] += 1u;
-    st[1 * c] += (d.fm >> 16) & 0xFFu;
-    if (!is_indel) st[2 * c] += bq;
-    st[3 * c] += (uint32_t)d.se;
-    if (d.fm & 16u) st[5 * c] += 1u; else st[4 * c] += 1u;
-    st[6 * c] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(st[6 * c]), t.posterm)));
-    st[7 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[7 * c]), d.nmfrac));
-    st[8 * c] += (uint32_t)d.mmq;
-    if (d.q2 > -1) { st[9 * c] += 1u; st[10 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[10 * c]), t.q2term)); }
-    st[11 * c] += (uint32_t)d.clen;
-    st[12 * c] = __float_as_uint(__fadd_rn(__uint_as_float(st[12 * c]), t.d3pterm));
+    return j;
+}
+__device__ __noinline__ int32_t rare_event(const PileupParams &P, int32_t head, uint32_t slot, int kind, int len, int32_t read, int qpos,
+                                           uint32_t bq, bool is_indel) {
+    const int32_t j = rare_find_or_append(P, head, slot, kind, len, read, qpos);
+    if ((int64_t)j < P.res.sec_cap) sec_accumulate(P, P.res.sec[j], read, qpos, bq, is_indel);
     return head;
 }
 
@@ -643,6 +660,11 @@ __device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci, in
 }
 
 __device__ __forceinline__ int2 lds_i2(const void *p) { return *reinterpret_cast<const int2 *>(p); }
+// row * n_slots + slot of the site this thread owns
+template <bool PER_LIB>
+__device__ __forceinline__ uint32_t slot_index(const PileupParams &P, const ChunkInfo &ci, const SiteState &S) {
+    return (uint32_t)((PER_LIB ? (int64_t)S.row * P.res.n_slots : 0) + ci.slot0 + (S.site - ci.pos0));
+}
 
 // The hot loop: one warp walks the chunk's reads in file order; lane = site.
 template <bool PER_LIB, bool STAGED>
@@ -704,7 +726,7 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // a tag the reference warns about is missing
         if (indel != 0) {
             const int32_t r = ci.r0 + (int)((ds - sb.desc) / 5);
-            S.sec_head = rare_event(P, S.sec_head, indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
+            S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
             if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
             if (indel > 0 && P.insertion_centric) continue;
         }
@@ -715,7 +737,7 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
         if (S.pbase == NO_BASE) S.pbase = base;
         if (base != S.pbase && S.sbase != NO_BASE && base != S.sbase) {   // third base class at this site: rare
-            S.sec_head = rare_event(P, S.sec_head, (int)base, 0, ci.r0 + (int)((ds - sb.desc) / 5), qpos, bq, false);
+            S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), (int)base, 0, ci.r0 + (int)((ds - sb.desc) / 5), qpos, bq, false);
             continue;
         }
         const int4 q1 = ds[1];                                   // mmq,clen,lclip,tpi
@@ -754,31 +776,56 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
     }
 }
 
-// last chunk of a tile: write the site's header + primary accumulators (coalesced SoA stores)
+// Packs one site's header + primary accumulators into the 8-word narrow record, or escapes it to a full-width pool record
+// (brc_device.cuh).  `st` = the 13 accumulators in print order.  Returns false when the pool overflowed (host retries).
+__device__ __forceinline__ void emit_packed(const ResultsDev &R, int64_t idx, uint32_t ncover, uint32_t npass, uint32_t flags, uint32_t pbase,
+                                            int32_t sec_head, const uint32_t (&st)[N_STATS]) {
+    const uint32_t pcode = pbase < 6u ? pbase : PB_NONE;
+    const bool narrow = ncover <= 255u && st[1] <= 0xFFFFu && st[2] <= 0xFFFFu && st[3] <= 0xFFFFu && st[11] <= 0xFFFFu && st[8] <= 0xFFFFu;
+    uint32_t w[N_WORDS];
+    if (narrow) {
+        w[0] = ncover | (npass << 8) | (st[0] << 16) | (st[4] << 24);
+        w[1] = pcode | ((flags & 1u) << 3) | (sec_head >= 0 ? 16u : 0u) | (st[9] << 8) | (st[1] << 16);
+        w[2] = st[2] | (st[3] << 16);
+        w[3] = st[11] | (st[8] << 16);
+        w[4] = st[6]; w[5] = st[7]; w[6] = st[10]; w[7] = st[12];
+    } else {
+        const int32_t j = atomicAdd(R.sec_count, 1);
+        if ((int64_t)j < R.sec_cap) {
+            SecRec &r = R.sec[j];
+            r.slot = (uint32_t)idx; r.next = sec_head; r.kind_len = (KIND_WIDE + pcode) | (ncover << 8); r.read = (int32_t)flags; r.qpos = (int32_t)npass;
+#pragma unroll
+            for (int k = 0; k < N_STATS; ++k) r.stats[k] = st[k];
+        }
+        w[0] = 0u; w[1] = PB_ESCAPE | ((flags & 1u) << 3) | 16u; w[2] = w[3] = w[4] = w[5] = w[6] = w[7] = 0u;
+    }
+    const int64_t stride = (int64_t)R.n_rows * R.n_slots;
+    uint32_t *dst = R.words + idx;
+#pragma unroll
+    for (int k = 0; k < N_WORDS; ++k) dst[k * stride] = w[k];     // each a fully-coalesced 128-byte line per warp
+}
+
+// last chunk of a tile: write the site's packed record (coalesced SoA stores)
 template <bool PER_LIB>
 __device__ __forceinline__ void site_emit(const PileupParams &P, uint32_t (*sacc)[TILE], const ChunkInfo &ci, SiteState &S, int tid) {
     if (S.site < 0) return;
     const ResultsDev &R = P.res;
     int32_t sec_head = S.sec_head;
+    const int64_t idx = (PER_LIB ? (int64_t)S.row * R.n_slots : 0) + ci.slot0 + (S.site - ci.pos0);
     if (S.sbase != NO_BASE) {   // move the second base class into the record pool
         const int32_t j = atomicAdd(R.sec_count, 1);
         if ((int64_t)j < R.sec_cap) {
-            R.sec_next[j] = sec_head; R.sec_kind[j] = (uint8_t)S.sbase; R.sec_len[j] = 0; R.sec_read[j] = 0; R.sec_qpos[j] = 0;
+            SecRec &r = R.sec[j];
+            r.slot = (uint32_t)idx; r.next = sec_head; r.kind_len = S.sbase; r.read = 0; r.qpos = 0;
 #pragma unroll
-            for (int k = 0; k < N_STATS; ++k) R.sec_stats[(int64_t)k * R.sec_cap + j] = sacc[k][tid];
+            for (int k = 0; k < N_STATS; ++k) r.stats[k] = sacc[k][tid];
             sec_head = j;
         }
     }
-    const int64_t idx = (PER_LIB ? (int64_t)S.row * R.n_slots : 0) + ci.slot0 + (S.site - ci.pos0);
-    const int64_t stride = (int64_t)R.n_rows * R.n_slots;
     const Acc &a = S.acc;
-    R.ncover[idx] = S.ncover; R.npass[idx] = S.npass; R.flags[idx] = (uint8_t)(PER_LIB ? S.flags : 0u); R.pbase[idx] = (uint8_t)S.pbase;
-    R.sec_head[idx] = sec_head;
-    uint32_t *ps = R.pstats + idx;
-    ps[0 * stride] = a.count; ps[1 * stride] = a.mapq; ps[2 * stride] = a.baseq; ps[3 * stride] = a.se;
-    ps[4 * stride] = a.plus; ps[5 * stride] = a.count - a.plus; ps[6 * stride] = __float_as_uint(__double2float_rn(a.posd));
-    ps[7 * stride] = __float_as_uint(a.nmf); ps[8 * stride] = a.mmqs; ps[9 * stride] = a.nq2;
-    ps[10 * stride] = __float_as_uint(a.q2d); ps[11 * stride] = a.clip; ps[12 * stride] = __float_as_uint(a.d3p);
+    const uint32_t st[N_STATS] = {a.count, a.mapq, a.baseq, a.se, a.plus, a.count - a.plus, __float_as_uint(__double2float_rn(a.posd)),
+                                  __float_as_uint(a.nmf), a.mmqs, a.nq2, __float_as_uint(a.q2d), a.clip, __float_as_uint(a.d3p)};
+    emit_packed(R, idx, S.ncover, S.npass, PER_LIB ? S.flags : 0u, S.pbase, sec_head, st);
 }
 
 template <bool PER_LIB>
@@ -946,58 +993,6 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
 //            statistic-0 thread.
 // Integer statistics go through the same ordered loop: it keeps one code path and costs one predicated add.
 // ---------------------------------------------------------------------------------------------
-// rare_event split in two for deep_site_kernel, where one thread replays every indel event of a (site, library):
-// find-or-append of the allele's record (a walk of dependent global loads — deep_site_kernel caches the result in shared
-// memory), and the accumulation with the 13 accumulator loads issued together.  Same arithmetic as rare_event.
-__device__ __noinline__ int32_t rare_find_or_append(const PileupParams &P, int32_t &head, int kind, int len, int32_t read, int qpos) {
-    const ResultsDev &S = P.res;
-    int32_t j = head;
-    while (j >= 0) {
-        if (S.sec_kind[j] == (uint8_t)kind && S.sec_len[j] == len) {
-            if (kind != KIND_INS) break;
-            const uint64_t oa = P.seq_off[read], ob = P.seq_off[S.sec_read[j]];
-            const int qb = S.sec_qpos[j];
-            bool same = true;
-            for (int k = 1; k <= len && same; ++k)
-                same = canonical16(seq_nib(P.seq, oa, qpos + k)) == canonical16(seq_nib(P.seq, ob, qb + k));
-            if (same) break;
-        }
-        j = S.sec_next[j];
-    }
-    if (j < 0) {
-        j = atomicAdd(S.sec_count, 1);
-        if ((int64_t)j >= S.sec_cap) return j;   // overflow: host sees sec_count > cap and retries with a larger pool
-        S.sec_next[j] = head; S.sec_kind[j] = (uint8_t)kind; S.sec_len[j] = len; S.sec_read[j] = read; S.sec_qpos[j] = qpos;
-#pragma unroll
-        for (int k = 0; k < N_STATS; ++k) S.sec_stats[(int64_t)k * S.sec_cap + j] = 0u;
-        head = j;
-    }
-    return j;
-}
-__device__ __noinline__ void rare_accumulate(const PileupParams &P, int32_t j, int32_t read, int qpos, uint32_t bq, bool is_indel) {
-    const ResultsDev &S = P.res;
-    const ReadDesc d = P.desc[read];
-    const Terms t = event_terms(false, qpos, d.q2, d.tpi, d.lclip, d.clen, d.fl, d.fclen, 0.f, 0.f);
-    uint32_t *st = S.sec_stats + j;
-    const int64_t c = S.sec_cap;
-    uint32_t v[N_STATS];
-#pragma unroll
-    for (int k = 0; k < N_STATS; ++k) v[k] = st[k * c];          // 13 independent loads in flight, then 13 stores
-    v[0] += 1u;
-    v[1] += (d.fm >> 16) & 0xFFu;
-    if (!is_indel) v[2] += bq;
-    v[3] += (uint32_t)d.se;
-    if (d.fm & 16u) v[5] += 1u; else v[4] += 1u;
-    v[6] = __float_as_uint(__double2float_rn(__dadd_rn((double)__uint_as_float(v[6]), t.posterm)));
-    v[7] = __float_as_uint(__fadd_rn(__uint_as_float(v[7]), d.nmfrac));
-    v[8] += (uint32_t)d.mmq;
-    if (d.q2 > -1) { v[9] += 1u; v[10] = __float_as_uint(__fadd_rn(__uint_as_float(v[10]), t.q2term)); }
-    v[11] += (uint32_t)d.clen;
-    v[12] = __float_as_uint(__fadd_rn(__uint_as_float(v[12]), t.d3pterm));
-#pragma unroll
-    for (int k = 0; k < N_STATS; ++k) st[k * c] = v[k];
-}
-
 #ifdef BRC_DEEP_PROFILE
 __device__ unsigned long long g_deepprof[8];
 #endif
@@ -1038,7 +1033,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // one indel event of a group (called by the group's read_count owner, in file order)
-__device__ __forceinline__ void deep_indel_event(const PileupParams &P, DeepSmem &sm, int og, int32_t &sec_head, int indel, int32_t read, int qpos, uint32_t bq) {
+__device__ __forceinline__ void deep_indel_event(const PileupParams &P, DeepSmem &sm, int og, uint32_t slot, int32_t &sec_head, int indel, int32_t read, int qpos, uint32_t bq) {
     const int kind = indel > 0 ? KIND_INS : KIND_DEL, len = indel > 0 ? indel : -indel;
     const bool cacheable = len <= 127 && (kind == KIND_DEL || len <= 8);
     uint32_t key = 0u;
@@ -1053,10 +1048,10 @@ __device__ __forceinline__ void deep_indel_event(const PileupParams &P, DeepSmem
     const uint32_t nc = sm.icount[og];
     if (cacheable) for (uint32_t e = 0; e < nc; ++e) if (sm.ikey[og][e] == key) j = sm.irec[og][e];
     if (j < 0) {
-        j = rare_find_or_append(P, sec_head, kind, len, read, qpos);
+        j = rare_find_or_append(P, sec_head, slot, kind, len, read, qpos);
         if (cacheable && (int64_t)j < P.res.sec_cap && nc < (uint32_t)DEEP_ICACHE) { sm.ikey[og][nc] = key; sm.irec[og][nc] = j; sm.icount[og] = nc + 1u; }
     }
-    if ((int64_t)j < P.res.sec_cap) rare_accumulate(P, j, read, qpos, bq, true);
+    if ((int64_t)j < P.res.sec_cap) sec_accumulate(P, P.res.sec[j], read, qpos, bq, true);
 }
 
 // this thread's read of the block starting at `blk` -> its own slots of stage st (no other thread touches them)
@@ -1102,6 +1097,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
     }
     uint32_t acc_u = 0u; float acc_f = 0.0f; double acc_d = 0.0;
     uint32_t pbase = NO_BASE; int32_t sec_head = -1;
+    const uint32_t oslot = owner ? (uint32_t)((int64_t)(og % n_rows) * P.res.n_slots + ti.slot0 + og / n_rows) : 0u;   // row * n_slots + slot of the owner's group
     uint32_t warn_nm = 0u, warn_sm = 0u;
 #ifdef BRC_DEEP_PROFILE
     long long prof[6] = {0, 0, 0, 0, 0, 0};
@@ -1246,7 +1242,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
             const uint32_t want = 16u | pbase;  // (m & 0x17) == want  <=>  base event of the primary class
             const bool is0 = oj == 0;
             // indel-only events before the first base event (insertion-centric): still the read_count owner's to replay
-            if (is0) for (uint32_t k = 0; k < i; ++k) { const uint32_t m = mp[k]; if (m & 8u) deep_indel_event(P, sm, og, sec_head, sm.eindel[b0 + k], sm.eread[b0 + k], sm.eqpos[b0 + k], m >> 8); }
+            if (is0) for (uint32_t k = 0; k < i; ++k) { const uint32_t m = mp[k]; if (m & 8u) deep_indel_event(P, sm, og, oslot, sec_head, sm.eindel[b0 + k], sm.eread[b0 + k], sm.eqpos[b0 + k], m >> 8); }
             // 32 events at a time, branch-free: a non-primary event adds 0 (exact: the sums are non-negative) and sets a bit;
             // the few marked events are then replayed in order — other base classes into their shared-memory cells, indel
             // alleles (separate keys, so their order relative to base events is immaterial) into the record pool
@@ -1277,7 +1273,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
                 if (is0) while (im) {
                     const uint32_t q = (uint32_t)__ffs(im) - 1u; im &= im - 1u;
                     const uint32_t slot = b0 + c0 + q;
-                    deep_indel_event(P, sm, og, sec_head, sm.eindel[slot], sm.eread[slot], sm.eqpos[slot], mq[q] >> 8);
+                    deep_indel_event(P, sm, og, oslot, sec_head, sm.eindel[slot], sm.eread[slot], sm.eqpos[slot], mq[q] >> 8);
                 }
                 while (nm) {
                     const uint32_t q = (uint32_t)__ffs(nm) - 1u; nm &= nm - 1u;
@@ -1306,7 +1302,8 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
             const ResultsDev &R = P.res;
             const int32_t j = atomicAdd(R.sec_count, 1);
             if ((int64_t)j < R.sec_cap) {
-                R.sec_next[j] = sec_head; R.sec_kind[j] = (uint8_t)c; R.sec_len[j] = 0; R.sec_read[j] = 0; R.sec_qpos[j] = 0;
+                SecRec &r = R.sec[j];
+                r.slot = oslot; r.next = sec_head; r.kind_len = (uint32_t)c; r.read = 0; r.qpos = 0;
                 sec_head = j;
             }
             sm.recj[og] = j;
@@ -1316,24 +1313,21 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
             const int32_t j = sm.recj[og];
             if ((int64_t)j < P.res.sec_cap) {
                 const unsigned long long cell = sm.other[c][tid];
-                P.res.sec_stats[(int64_t)oj * P.res.sec_cap + j] = kind == 2 ? __float_as_uint(__double2float_rn(__longlong_as_double((long long)cell))) : (uint32_t)cell;
+                P.res.sec[j].stats[oj] = kind == 2 ? __float_as_uint(__double2float_rn(__longlong_as_double((long long)cell))) : (uint32_t)cell;
             }
         }
         __syncthreads();
     }
-    // ---- emit: the layout site_emit writes ----
-    if (owner) {
-        const ResultsDev &R = P.res;
-        const int sg = og / n_rows, row = og - sg * n_rows;
-        const int64_t idx = (int64_t)row * R.n_slots + ti.slot0 + sg;
-        const int64_t stride = (int64_t)R.n_rows * R.n_slots;
-        const uint32_t v = kind == 2 ? __float_as_uint(__double2float_rn(acc_d)) : (kind == 1 ? __float_as_uint(acc_f) : acc_u);
-        R.pstats[(int64_t)oj * stride + idx] = v;
-        if (oj == 0) {
-            R.ncover[idx] = sm.ncover[og]; R.npass[idx] = sm.npass[og];
-            R.flags[idx] = (uint8_t)((PER_LIB && sm.first_libless[sg] != 0x7fffffff) ? 1u : 0u);
-            R.pbase[idx] = (uint8_t)pbase; R.sec_head[idx] = sec_head;
-        }
+    // ---- emit: the packed record site_emit writes; the 13 owners of a group hand their sums to its read_count owner ----
+    uint32_t *scr = sm.meta;                                   // free after the last block: [group][16] scratch
+    if (owner) scr[og * 16 + oj] = kind == 2 ? __float_as_uint(__double2float_rn(acc_d)) : (kind == 1 ? __float_as_uint(acc_f) : acc_u);
+    __syncthreads();
+    if (owner && oj == 0) {
+        const int sg = og / n_rows;
+        uint32_t st[N_STATS];
+#pragma unroll
+        for (int k = 0; k < N_STATS; ++k) st[k] = scr[og * 16 + k];
+        emit_packed(P.res, (int64_t)oslot, sm.ncover[og], sm.npass[og], (PER_LIB && sm.first_libless[sg] != 0x7fffffff) ? 1u : 0u, pbase, sec_head, st);
     }
     for (int o = 16; o; o >>= 1) { warn_sm += __shfl_xor_sync(0xffffffffu, warn_sm, o); warn_nm += __shfl_xor_sync(0xffffffffu, warn_nm, o); }
     if (lane == 0) {

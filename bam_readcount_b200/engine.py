@@ -59,10 +59,24 @@ class CResults(C.Structure):
                 ("sec_stats", C.c_void_p)]
 
 
+class CSecRecord(C.Structure):
+    _fields_ = [("slot", C.c_uint32), ("next", C.c_int32), ("kind_len", C.c_uint32), ("read", C.c_int32), ("qpos", C.c_int32),
+                ("stats", C.c_uint32 * 13)]
+
+
+class CPackedResults(C.Structure):
+    """brc_packed_results: the 32 B/site records the kernels write (include/brc_engine.h)."""
+    _fields_ = [("n_regions", C.c_int64), ("regions", C.POINTER(CRegion)), ("n_rows", C.c_int32), ("n_slots", C.c_int64),
+                ("words", C.c_void_p), ("n_sec", C.c_int64), ("sec", C.c_void_p), ("sec_count", C.c_void_p)]
+
+
+N_WORDS = 8
+SEC_RECORD_BYTES = 72
+
 EXPORTS = [
-    "brc_abi_version", "brc_create", "brc_destroy", "brc_last_error", "brc_strerror", "brc_set_reference", "brc_reset",
+    "brc_abi_version", "brc_create", "brc_destroy", "brc_last_error", "brc_strerror", "brc_set_reference", "brc_set_reference_device", "brc_reset",
     "brc_begin_region", "brc_push_read", "brc_push_reads", "brc_end_region", "brc_compute", "brc_get_results",
-    "brc_get_warning_counts", "brc_format_text", "brc_format_window", "brc_write_text", "brc_plan_device", "brc_run_device", "brc_device_results",
+    "brc_get_warning_counts", "brc_format_text", "brc_format_window", "brc_write_text", "brc_plan_device", "brc_run_device", "brc_device_packed_results", "brc_get_packed_results",
     "brc_fetch_device_results", "brc_last_launch_count", "brc_last_stage_ms", "brc_selftest_fastmath",
 ]
 
@@ -87,6 +101,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.brc_strerror.argtypes = [C.c_int]
     lib.brc_strerror.restype = C.c_char_p
     lib.brc_set_reference.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int64]
+    lib.brc_set_reference_device.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     lib.brc_reset.argtypes = [C.c_void_p]
     lib.brc_begin_region.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.brc_push_read.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint16, C.c_uint8, C.c_uint16, C.c_int32,
@@ -104,7 +119,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.brc_write_text.restype = C.c_int64
     lib.brc_plan_device.argtypes = [C.c_void_p, C.POINTER(CRegion), C.c_int64, C.c_int64, C.c_int64]
     lib.brc_run_device.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p]
-    lib.brc_device_results.argtypes = [C.c_void_p, C.POINTER(CResults)]
+    lib.brc_device_packed_results.argtypes = [C.c_void_p, C.POINTER(CPackedResults)]
+    lib.brc_get_packed_results.argtypes = [C.c_void_p, C.POINTER(CPackedResults)]
     lib.brc_fetch_device_results.argtypes = [C.c_void_p, C.c_void_p]
     lib.brc_selftest_fastmath.argtypes = [C.c_void_p, C.c_int32]
     lib.brc_selftest_fastmath.restype = C.c_int64
@@ -161,6 +177,24 @@ class Results:
             self._dump_region(g, pushed, refs, out, queues, per_lib)
         return "".join(out)
 
+    def dump_range(self, pushed: ReadBatch, refs: dict, region_index: int, pos_lo: int, pos_hi: int, read_offset: int = 0) -> str:
+        """Dump of the sites [pos_lo, pos_hi) of one region, starting with an empty deletion queue — what the oracle prints for
+        the region (pos_lo+1, pos_hi) whose halo is pos_lo.  ``pushed`` may be a suffix of the pushed stream: ``read_offset`` is the
+        stream index of its first read (insertion alleles are looked up in it)."""
+        g = dict(self.regions[region_index])
+        s0 = pos_lo - g["first_pos"]
+        assert 0 <= s0 and pos_hi <= g["first_pos"] + g["n_slots"]
+        g["slot_base"] += s0
+        g["first_pos"] = pos_lo
+        g["n_slots"] = pos_hi - pos_lo
+        out: List[str] = []
+        self._read_offset = read_offset
+        try:
+            self._dump_region(g, pushed, refs, out, [[] for _ in range(self.n_rows)], self.n_rows > 1 or getattr(self, "_per_lib", False))
+        finally:
+            self._read_offset = 0
+        return "".join(out)
+
     def _stat_str(self, v) -> str:
         return " ".join((f"{int(x):08x}" if k in _FLOAT_STATS else str(int(x))) for k, x in enumerate(v))
 
@@ -177,7 +211,7 @@ class Results:
             else:
                 ln = int(self.sec_len[j])
                 if k == KIND_INS:
-                    rd, qp = int(self.sec_read[j]), int(self.sec_qpos[j])
+                    rd, qp = int(self.sec_read[j]) - getattr(self, "_read_offset", 0), int(self.sec_qpos[j])
                     so = int(pushed.seq_off[rd])
                     al = "+"
                     for t in range(1, ln + 1):
@@ -226,6 +260,46 @@ class Results:
                     out.append(f"Q {row} {al} {self._stat_str(st)}\n")
                     extra += int(st[0])
             out.append(f"D {mapq_n + extra}\n")
+
+
+class PackedResults:
+    """Host copy of the PACKED records (include/brc_engine.h): 8 words per (row, slot) + 72-byte secondary records."""
+
+    def __init__(self, r: CPackedResults):
+        self.n_rows, self.n_slots = int(r.n_rows), int(r.n_slots)
+        rs = self.n_rows * self.n_slots
+        self.words = _np_view(r.words, rs * N_WORDS, np.uint32).reshape(N_WORDS, self.n_rows, self.n_slots).copy()
+        self.n_sec = int(r.n_sec)
+        self.sec = _np_view(r.sec, self.n_sec * (SEC_RECORD_BYTES // 4), np.uint32).reshape(self.n_sec, SEC_RECORD_BYTES // 4).copy()
+
+    def nbytes(self) -> int:
+        return int(self.words.nbytes + self.sec.nbytes)
+
+    def widen(self):
+        """numpy restatement of the engine's ensure_wide(): (ncover, npass, flags, pbase, pstats[13]) per (row, slot);
+        escaped sites are filled from their pool record."""
+        w = self.words
+        ncover = (w[0] & 0xFF).astype(np.uint32)
+        npass = ((w[0] >> 8) & 0xFF).astype(np.uint32)
+        count = ((w[0] >> 16) & 0xFF).astype(np.uint32)
+        plus = (w[0] >> 24).astype(np.uint32)
+        pc = (w[1] & 7).astype(np.uint8)
+        flags = ((w[1] >> 3) & 1).astype(np.uint8)
+        pbase = np.where(pc < 6, pc, NO_BASE).astype(np.uint8)
+        ps = np.stack([count, w[1] >> 16, w[2] & 0xFFFF, w[2] >> 16, plus, count - plus, w[4], w[5], w[3] >> 16, (w[1] >> 8) & 0xFF,
+                       w[6], w[3] & 0xFFFF, w[7]]).astype(np.uint32)
+        for j in range(self.n_sec):
+            rec = self.sec[j]
+            kind = int(rec[2]) & 0xFF
+            if kind < 8:
+                continue
+            row, slot = divmod(int(rec[0]), self.n_slots)
+            ncover[row, slot] = int(rec[2]) >> 8
+            npass[row, slot] = rec[4]
+            flags[row, slot] = int(rec[3]) & 1
+            pbase[row, slot] = kind - 8 if kind - 8 < 6 else NO_BASE
+            ps[:, row, slot] = rec[5:18]
+        return ncover, npass, flags, pbase, ps
 
 
 class Engine:
@@ -312,6 +386,36 @@ class Engine:
         buf = C.create_string_buffer(int(n) + 1)
         self.lib.brc_format_text(self.h, region, self._names_arr, buf, int(n) + 1)
         return buf.raw[:int(n)].decode("latin-1")
+
+    # ---- device-resident path (include/brc_engine.h "device-resident path") ---------------------------------
+    def set_reference_device(self, tid: int, name: str, chrom_len: int, win_beg: int, dev_ascii_ptr: int, win_len: int, stream_ptr: int):
+        self._check(self.lib.brc_set_reference_device(self.h, tid, name.encode(), chrom_len, win_beg, dev_ascii_ptr, win_len, stream_ptr))
+
+    def plan_device(self, regions: Sequence[CRegion], n_reads_cap: int, n_sec_cap: int = 0):
+        arr = (CRegion * len(regions))(*regions)
+        self._plan_keep = arr
+        self._check(self.lib.brc_plan_device(self.h, arr, len(regions), n_reads_cap, n_sec_cap))
+
+    def run_device(self, cbatch: CReadBatch, region_of_read_ptr: Optional[int], stream_ptr: int):
+        self._check(self.lib.brc_run_device(self.h, C.byref(cbatch), region_of_read_ptr, stream_ptr))
+
+    def device_packed(self) -> CPackedResults:
+        r = CPackedResults()
+        self._check(self.lib.brc_device_packed_results(self.h, C.byref(r)))
+        return r
+
+    def fetch_device_results(self, stream_ptr: int) -> Results:
+        self._check(self.lib.brc_fetch_device_results(self.h, stream_ptr))
+        r = CResults()
+        self._check(self.lib.brc_get_results(self.h, C.byref(r)))
+        res = Results(r)
+        res._per_lib = self.per_lib
+        return res
+
+    def packed(self) -> "PackedResults":
+        r = CPackedResults()
+        self._check(self.lib.brc_get_packed_results(self.h, C.byref(r)))
+        return PackedResults(r)
 
     def stage_ms(self, stage: int) -> float:
         return float(self.lib.brc_last_stage_ms(self.h, stage))

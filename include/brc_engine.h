@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BRC_ABI_VERSION 1
+#define BRC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BRC_API __attribute__((visibility("default")))
@@ -160,6 +160,40 @@ typedef struct {
     const uint32_t *sec_stats;  /* [BRC_N_STATS][n_sec] */
 } brc_results;
 
+/* PACKED results: what the kernels write and what crosses PCIe / NVLink (32 B per site instead of 66 B).
+ * Per (row, slot) eight u32 words, stored struct-of-arrays as words[w][row * n_slots + slot]:
+ *   W0  ncover[0:8) | npass[8:16) | count[16:24) | plus[24:32)                 (minus = count - plus)
+ *   W1  primary base code [0:3): 0..5 = "=ACGTN", 6 = none, 7 = ESCAPED | bit 3: flags bit0 (read without library) |
+ *       bit 4: the site has records in the secondary pool | nq2 [8:16) | sum_map_qualities [16:32)
+ *   W2  sum_base_qualities [0:16) | sum_single_ended_map_qualities [16:32)
+ *   W3  sum_of_clipped_lengths [0:16) | sum_of_mismatch_qualities [16:32)
+ *   W4..W7  IEEE float32 bits of sum_event_location, sum_number_of_mismatches, sum_q2_distance, sum_3p_distance
+ * A site whose counters do not fit (more than 255 spanning reads, a 16-bit sum overflowing) is ESCAPED: its words carry
+ * only the flag bits and its full-width primary is a secondary-pool record of kind BRC_KIND_WIDE + base code.
+ * Secondary-pool records (other base classes, indel alleles, escaped primaries), 72 bytes each, any order: */
+#define BRC_N_WORDS 8
+#define BRC_PB_NONE 6
+#define BRC_PB_ESCAPE 7
+#define BRC_KIND_WIDE 8           /* kinds 8..14: escaped primary with base code kind-8; then length = ncover, read = flags, qpos = npass */
+typedef struct {
+    uint32_t slot;                /* row * n_slots + slot */
+    int32_t next;                 /* device-internal chain link (ignore) */
+    uint32_t kind_len;            /* kind in bits [0:8), indel length in bits [8:32) */
+    int32_t read;                 /* representative read (index into the pushed stream) carrying the insertion bases */
+    int32_t qpos;                 /* its qpos: inserted bases are read bases qpos+1 .. qpos+len */
+    uint32_t stats[BRC_N_STATS];
+} brc_sec_record;
+typedef struct {
+    int64_t n_regions;
+    const brc_region *regions;
+    int32_t n_rows;
+    int64_t n_slots;
+    const uint32_t *words;        /* [BRC_N_WORDS][n_rows*n_slots] */
+    int64_t n_sec;                /* host view: records in use; device view: pool capacity */
+    const brc_sec_record *sec;
+    const int32_t *sec_count;     /* device view only: the pool's live counter (device pointer); NULL in the host view */
+} brc_packed_results;
+
 /* ---- lifecycle ------------------------------------------------------------------------- */
 BRC_API int brc_abi_version(void);
 BRC_API int brc_create(const brc_config *cfg, brc_engine **out);
@@ -172,6 +206,12 @@ BRC_API const char *brc_strerror(int status);
  * The window must cover every base the region's reads and deletion alleles touch. */
 BRC_API int brc_set_reference(brc_engine *e, int32_t tid, const char *contig_name, int64_t chrom_len, int64_t win_beg,
                       const char *seq, int64_t win_len);
+
+/* Same, from a window that already sits in DEVICE memory as ASCII (a generator or a device-side decoder wrote it): the
+ * encode kernel is enqueued on `stream` (a cudaStream_t), nothing is synchronised and no host copy is kept — the text
+ * emitter (brc_format_*) refuses regions of that contig until brc_set_reference supplies the characters. */
+BRC_API int brc_set_reference_device(brc_engine *e, int32_t tid, const char *contig_name, int64_t chrom_len, int64_t win_beg,
+                             const char *dev_ascii, int64_t win_len, void *stream);
 
 /* ---- region loop ----------------------------------------------------------------------- */
 BRC_API int brc_reset(brc_engine *e);                      /* drop all pushed regions/reads and results */
@@ -191,7 +231,8 @@ BRC_API int brc_end_region(brc_engine *e);
  * pileup/accumulate kernel, D2H.  Reads not admitted by the pileup buffer (tid<0, FUNMAP,
  * the -d rule of V:htslib-1.10/sam.c:4491) are dropped on the host while batching. */
 BRC_API int brc_compute(brc_engine *e);
-BRC_API int brc_get_results(brc_engine *e, brc_results *out);
+BRC_API int brc_get_results(brc_engine *e, brc_results *out);      /* full-width view, expanded from the packed records on first use */
+BRC_API int brc_get_packed_results(brc_engine *e, brc_packed_results *out);   /* the records as they came off the device (pinned host memory) */
 /* counts of the reference's per-event warnings: [0]=SM_TAG_MISSING [1]=NM_TAG_MISSING
  * [2]=Zm_TAG_MISSING (always 0) [3]=LIBRARY_UNAVAILABLE (R:src/lib/bamrc/ReadWarnings.hpp:12-18) */
 BRC_API int brc_get_warning_counts(brc_engine *e, int64_t out[4]);
@@ -215,13 +256,14 @@ BRC_API int64_t brc_write_text(brc_engine *e, int64_t region_index, int64_t firs
  * brc_plan_device: fix the region geometry (host array of n_regions regions with read_lo/hi,
  * slot_base, first_pos, n_slots filled) and size the outputs.  brc_run_device: launch the
  * kernels on `stream` (a cudaStream_t) over a batch whose pointers are DEVICE pointers and the
- * reference window set by brc_set_reference; results stay on the device.  brc_device_results
- * returns device pointers in a brc_results.  brc_fetch_device_results copies them to the host
- * arrays brc_get_results exposes. */
+ * reference window set by brc_set_reference; results stay on the device.  brc_device_packed_results
+ * returns DEVICE pointers to the packed records (what a multi-GPU run sends over NCCL for the ordered
+ * emit).  brc_fetch_device_results copies them to the host arrays brc_get_results /
+ * brc_get_packed_results expose. */
 BRC_API int brc_plan_device(brc_engine *e, const brc_region *regions, int64_t n_regions, int64_t n_reads_cap,
                     int64_t n_sec_cap);
 BRC_API int brc_run_device(brc_engine *e, const brc_read_batch *dev_batch, const int32_t *dev_region_of_read, void *stream);
-BRC_API int brc_device_results(brc_engine *e, brc_results *out);
+BRC_API int brc_device_packed_results(brc_engine *e, brc_packed_results *out);
 BRC_API int brc_fetch_device_results(brc_engine *e, void *stream);
 /* Self-test of the kernels' exact-arithmetic shortcuts (reciprocal division, float<->double bit casts)
  * against the IEEE intrinsics for every divisor 1..max_b; returns the number of mismatches (0 = ok). */

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for s in decl:
         assert hasattr(lib, s), f"{s} declared in include/brc_engine.h but not exported"
     assert sorted(engine.EXPORTS) == decl
-    assert lib.brc_abi_version() == 1
+    assert lib.brc_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
