@@ -92,10 +92,16 @@ CLI = os.path.join(HERE, "brc-readcount")
 def build_cli(force: bool = False) -> str:
     """The C++ host binary (same CLI / STDOUT as bam-readcount) on top of libbrc_engine.so."""
     src = os.path.join(CSRC, "brc_cli.cpp")
-    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+    hts_a = os.path.join(HERE, "third_party", "htslib", "libhts.a")
+    newest = max([os.path.getmtime(src), os.path.getmtime(LIB)] + ([os.path.getmtime(hts_a)] if os.path.exists(hts_a) else []))
+    if not force and os.path.exists(CLI) and os.path.getmtime(CLI) >= newest:
         return CLI
     cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI, src, "-I", os.path.join(HERE, "..", "include"),
-           "-L", HERE, "-lbrc_engine", "-lz", "-Wl,-rpath,$ORIGIN"]
+           "-L", HERE, "-lbrc_engine"]
+    hts = os.path.join(HERE, "third_party", "htslib")          # tools/build_htslib.sh: htslib 1.10 as vendored with the reference (CRAM only)
+    if os.path.exists(os.path.join(hts, "libhts.a")):
+        cmd += ["-DBRC_WITH_HTSLIB", "-I", hts, os.path.join(hts, "libhts.a"), "-lpthread"]
+    cmd += ["-lz", "-Wl,-rpath,$ORIGIN"]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout)

@@ -2,7 +2,9 @@
 // (R:src/exe/bam-readcount/bamreadcount.cpp:421-670), with the pileup hot path routed through
 // libbrc_engine.so (include/brc_engine.h).  File decode stays on the host, as the north star says:
 // a small BGZF/BAM/BAI/FASTA reader written against the SAM specification (zlib for inflate);
-// htslib is not linked.  CRAM input is not supported by this host.
+// htslib is not needed for BAM.  CRAM input (R:test-data/cram_site_test.sh, BASELINE config 2b) is decoded through htslib when the
+// host is built with -DBRC_WITH_HTSLIB against a libhts.a (tools/build_htslib.sh builds the copy vendored with the reference,
+// htslib 1.10); without it a .cram argument is refused with a message.
 //
 // Mirrors, region by region, the reference's two loops:
 //   -l site list : R:...:574-608  (d.beg=beg-1, d.end=end, queues cleared per region)
@@ -26,6 +28,11 @@
 #include <unistd.h>
 
 #include "../../include/brc_engine.h"
+#ifdef BRC_WITH_HTSLIB
+#include <functional>
+#include <htslib/sam.h>
+#include <htslib/hts.h>
+#endif
 
 namespace {
 
@@ -39,6 +46,7 @@ struct Bgzf {
     uint64_t next_coff = 0;      // compressed offset of the next block
     size_t upos = 0;             // position inside `block`
     bool eof = false;
+    bool error = false;          // a block failed to inflate / a header is malformed / the file ends inside a block: not a clean EOF
     // read-ahead: a span of consecutive blocks is read with one fread and inflated by several threads
     struct Ahead { uint64_t coff, next; std::vector<uint8_t> data; bool ok; };
     std::vector<Ahead> ahead; size_t ahead_pos = 0;
@@ -84,7 +92,8 @@ struct Bgzf {
         if (fseeko(fp, (off_t)coff, SEEK_SET) != 0) return false;
         raw.resize(span_blocks * 65536 + 65536);
         const size_t got = std::fread(raw.data(), 1, raw.size(), fp);
-        if (got < 18) { eof = true; return false; }
+        if (got == 0) { eof = true; return false; }                      // clean end of file at a block boundary
+        if (got < 18) { eof = true; error = true; return false; }        // a fragment of a block header
         struct Job { size_t off, hdr, total; };
         std::vector<Job> jobs;
         for (size_t o = 0; o < got && jobs.size() < span_blocks;) {
@@ -92,7 +101,7 @@ struct Bgzf {
             if (!tot || o + tot > got) break;
             jobs.push_back({o, hdr, tot}); o += tot;
         }
-        if (jobs.empty()) return false;
+        if (jobs.empty()) { error = true; return false; }                // bytes are there but no whole, well-formed block
         ahead.resize(jobs.size());
         auto work = [&](size_t t) {
             for (size_t j = t; j < jobs.size(); j += (size_t)n_threads) {
@@ -120,7 +129,7 @@ struct Bgzf {
             if (!found && !fill_ahead(coff)) { block.clear(); upos = 0; return false; }
         }
         Ahead &a = ahead[ahead_pos];
-        if (!a.ok) return false;
+        if (!a.ok) { error = true; return false; }
         block = a.data;                 // keep the span entry intact: sorted site lists revisit blocks
         block_coff = a.coff; next_coff = a.next; upos = 0; eof = false;
         ++ahead_pos;
@@ -242,9 +251,10 @@ int64_t aux_int(const uint8_t *p, char t) {
 
 bool read_record(Bgzf &bz, Rec &r) {
     int32_t bs;
-    if (!bz.read(&bs, 4) || bs < 32) return false;
+    if (!bz.read(&bs, 4)) return false;                                   // EOF (clean unless bz.error)
+    if (bs < 32) { bz.error = true; return false; }                       // not a BAM record
     r.data.resize((size_t)bs);
-    if (!bz.read(r.data.data(), (size_t)bs)) return false;
+    if (!bz.read(r.data.data(), (size_t)bs)) { bz.error = true; return false; }   // file ends inside a record
     const uint8_t *d = r.data.data();
     int32_t refid, pos, l_seq; uint8_t l_rn, mapq; uint16_t n_cig, flag;
     std::memcpy(&refid, d, 4); std::memcpy(&pos, d + 4, 4); l_rn = d[8]; mapq = d[9];
@@ -334,6 +344,145 @@ struct RegionFetcher {
     }
 };
 
+#ifdef BRC_WITH_HTSLIB
+// ------------------------------------------------------------------------------------------
+// CRAM (or any htslib-readable alignment file) through htslib: header, index, and samfetch()'s iterator per region.
+// Records are re-laid-out as the Rec the BAM reader produces, so everything downstream is shared.
+// ------------------------------------------------------------------------------------------
+struct HtsSource {
+    samFile *fp = nullptr; bam_hdr_t *hdr = nullptr; hts_idx_t *idx = nullptr; bam1_t *b = nullptr;
+    uint64_t n_seeks = 0, n_decoded = 0; bool error = false;
+    ~HtsSource() { if (b) bam_destroy1(b); if (idx) hts_idx_destroy(idx); if (hdr) bam_hdr_destroy(hdr); if (fp) sam_close(fp); }
+    bool open(const std::string &path, const std::string &fasta, BamFile &meta) {
+        fp = sam_open(path.c_str(), "r");
+        if (!fp) return false;
+        if (!fasta.empty() && hts_set_fai_filename(fp, (fasta + ".fai").c_str()) != 0) return false;   // R:bamreadcount.cpp:503-523
+        hdr = sam_hdr_read(fp);
+        if (!hdr) return false;
+        meta.text.assign(hdr->text ? hdr->text : "", hdr->text ? hdr->l_text : 0);
+        for (int i = 0; i < hdr->n_targets; ++i) { meta.names.push_back(hdr->target_name[i]); meta.lens.push_back((int32_t)hdr->target_len[i]); meta.tid_of[hdr->target_name[i]] = i; }
+        b = bam_init1();
+        return true;
+    }
+    bool load_index(const std::string &path) { idx = sam_index_load(fp, path.c_str()); return idx != nullptr; }
+    void fetch(int tid, int64_t fbeg, int64_t fend, const std::function<void(const Rec &)> &emit) {
+        hts_itr_t *it = sam_itr_queryi(idx, tid, fbeg, fend);
+        if (!it) return;
+        ++n_seeks;
+        Rec r; int ret;
+        while ((ret = sam_itr_next(fp, it, b)) >= 0) {
+            ++n_decoded;
+            const bam1_core_t &c = b->core;
+            r.tid = c.tid; r.pos = (int32_t)c.pos; r.l_qseq = c.l_qseq; r.flag = c.flag; r.mapq = c.qual; r.n_cigar = c.n_cigar;
+            r.data.assign(32, 0); r.data.insert(r.data.end(), b->data, b->data + b->l_data);      // qname at +32, as in a BAM record body
+            const uint8_t *d = r.data.data() + 32;
+            r.cigar = (const uint32_t *)(d + c.l_qname); r.seq = d + c.l_qname + 4 * (size_t)c.n_cigar; r.qual = r.seq + ((size_t)c.l_qseq + 1) / 2;
+            uint8_t *p;
+            r.nm = (p = bam_aux_get(b, "NM")) ? (int32_t)bam_aux2i(p) : BRC_TAG_ABSENT;
+            r.sm = (p = bam_aux_get(b, "SM")) ? (int32_t)bam_aux2i(p) : BRC_TAG_ABSENT;
+            r.has_rg = (p = bam_aux_get(b, "RG")) != nullptr && *p == 'Z';
+            if (r.has_rg) r.rg = (const char *)(p + 1);
+            r.endpos = rec_endpos(r);
+            emit(r);
+        }
+        if (ret < -1) error = true;
+        hts_itr_destroy(it);
+    }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------
+// Per-read warning lines (R:src/lib/bamrc/ReadWarnings.hpp:12-50; call sites R:BasicStat.cpp:85,100 and R:bamreadcount.cpp:282).
+// The engine returns per-type event COUNTS; the text names reads, in the order the reference meets the events: region by
+// region, site by site, spanning reads in file order, and inside one event process_read's own order (SM before NM; an
+// indel event calls process_read for the indel key and again for the base key).  The host replays exactly that walk over the
+// reads that can warn at all (no NM tag, proper pair without SM tag, no library under -p) until every type has used up its
+// -w budget, then stops collecting.  With -w -1 the reference prints one line per offending EVENT without bound; this host
+// prints the first 1000 per type and then the engine's exact total (the one documented STDERR difference).
+// ------------------------------------------------------------------------------------------
+struct Warner {
+    enum { SM = 0, NM = 1, ZM = 2, LIB = 3, NT = 4 };
+    struct Cand { int32_t pos; int64_t endpos; uint16_t flag; uint8_t mapq; bool no_nm, no_sm, no_lib; std::vector<uint32_t> cigar; std::vector<uint8_t> qual; std::string qname; };
+    struct Reg { int tid, beg, end; bool skip_halo; size_t c0, c1; };
+    long long max_per_type; bool unlimited; int min_mapq, min_bq; bool per_lib, ic;
+    long long counts[NT] = {0, 0, 0, 0};
+    std::vector<Cand> cands; std::vector<Reg> regs;
+    Warner(long long mw, int q, int b, bool p, bool i) : max_per_type(mw < 0 ? 1000 : mw), unlimited(mw < 0), min_mapq(q), min_bq(b), per_lib(p), ic(i) {}
+    bool budget_left() const { return counts[SM] < max_per_type || counts[NM] < max_per_type || (per_lib && counts[LIB] < max_per_type); }
+    bool collecting() const { return max_per_type > 0 && budget_left(); }
+    void begin_region(int tid, int beg, int end, bool skip_halo) { regs.push_back({tid, beg, end, skip_halo, cands.size(), cands.size()}); }
+    void consider(const Rec &r, bool no_lib) {
+        if (!collecting() || (r.flag & 4) || regs.empty()) return;
+        const bool no_nm = r.nm == BRC_TAG_ABSENT, no_sm = (r.flag & 2) && r.sm == BRC_TAG_ABSENT;
+        if (!no_nm && !no_sm && !(per_lib && no_lib)) return;
+        Cand c; c.pos = r.pos; c.endpos = r.endpos; c.flag = r.flag; c.mapq = r.mapq; c.no_nm = no_nm; c.no_sm = no_sm; c.no_lib = per_lib && no_lib;
+        c.cigar.assign(r.cigar, r.cigar + r.n_cigar); c.qual.assign(r.qual, r.qual + r.l_qseq);
+        c.qname = (const char *)(r.data.data() + 32);
+        cands.push_back(std::move(c)); regs.back().c1 = cands.size();
+    }
+    void emit(int type, const std::string &qname) {
+        static const char *msg[NT] = {"Couldn't find single-end mapping quality. Check to see if the SM tag is in BAM.",
+                                      "Couldn't find number of mismatches. Check to see if the NM tag is in BAM.",
+                                      "Couldn't find the generated tag.",
+                                      "Library unavailable. Check to make sure the LB tag is present in the @RG entries of the header."};
+        ++counts[type];
+        if (counts[type] > max_per_type) return;
+        std::fprintf(stderr, "WARNING: In read %s: %s\n", qname.c_str(), msg[type]);
+        if (!unlimited && counts[type] == max_per_type) std::fprintf(stderr, "The previous warning has been emitted %lld times and will be disabled.\n", counts[type]);
+    }
+    // stateless resolve_cigar2 (V:htslib-1.10/sam.c:3964-4041): qpos / is_del / indel of `site` in a read
+    static bool resolve(const Cand &c, int64_t site, int &qpos, int &indel) {
+        int64_t x = c.pos; int y = 0; size_t k = 0; uint32_t op = 0; int len = 0; const size_t n = c.cigar.size();
+        auto refop = [](uint32_t o) { return o == 0 || o == 2 || o == 3 || o == 7 || o == 8; };
+        auto matchop = [](uint32_t o) { return o == 0 || o == 7 || o == 8; };
+        for (; k < n; ++k) {
+            op = c.cigar[k] & 0xF; len = (int)(c.cigar[k] >> 4);
+            if (refop(op)) { if (site < x + len) break; x += len; if (matchop(op)) y += len; }
+            else if (op == 1 || op == 4) y += len;
+        }
+        indel = 0;
+        if (k >= n) return false;
+        const bool is_del = !matchop(op);
+        qpos = is_del ? y : y + (int)(site - x);
+        if (x + len - 1 == site && k + 1 < n) {
+            const uint32_t op2 = c.cigar[k + 1] & 0xF; const int l2 = (int)(c.cigar[k + 1] >> 4);
+            if (op2 == 2) indel = -l2;
+            else if (op2 == 1) indel = l2;
+            else if (op2 == 6) { int l3 = 0; for (size_t m = k + 2; m < n; ++m) { const uint32_t o3 = c.cigar[m] & 0xF; if (o3 == 1) l3 += (int)(c.cigar[m] >> 4); else if (refop(o3)) break; } if (l3 > 0) indel = l3; }
+        }
+        return !is_del;
+    }
+    void replay() {
+        for (const Reg &g : regs) {
+            if (!budget_left()) break;
+            if (g.c0 == g.c1) continue;
+            const int64_t first = g.skip_halo ? g.beg : std::max(g.beg - 1, 0);
+            size_t lo = g.c0;
+            for (int64_t p = std::max<int64_t>(first, cands[g.c0].pos); p < g.end && budget_left(); ++p) {
+                while (lo < g.c1 && cands[lo].endpos <= p) ++lo;          // leading reads that ended (later ones are re-checked below)
+                if (lo >= g.c1) break;
+                if (cands[lo].pos > p) { p = cands[lo].pos - 1; continue; }
+                for (size_t i = lo; i < g.c1 && cands[i].pos <= p; ++i) {
+                    const Cand &c = cands[i];
+                    if (c.endpos <= p) continue;
+                    if (c.no_lib) { emit(LIB, c.qname); break; }            // pileup_func returns: nothing after it at this site (R:...:281-284)
+                    int qpos = 0, indel = 0;
+                    if (!resolve(c, p, qpos, indel)) continue;               // is_del
+                    if ((int)c.mapq < min_mapq || qpos >= (int)c.qual.size() || (int)c.qual[(size_t)qpos] < min_bq || (c.flag & (4 | 256 | 512 | 1024))) continue;
+                    const int calls = (indel != 0 ? 1 : 0) + ((indel < 1 || !ic) ? 1 : 0);
+                    for (int k = 0; k < calls; ++k) { if (c.no_sm) emit(SM, c.qname); if (c.no_nm) emit(NM, c.qname); }
+                }
+            }
+        }
+        cands.clear(); regs.clear();
+    }
+    void finish(const int64_t engine_counts[4]) const {
+        if (!unlimited) return;
+        static const char *nm[NT] = {"SM tag missing", "NM tag missing", "generated tag missing", "library unavailable"};
+        for (int t = 0; t < NT; ++t) if (engine_counts[t] > max_per_type) std::fprintf(stderr, "WARNING: %s: %lld events in total (only the first %lld are listed)\n", nm[t], (long long)engine_counts[t], max_per_type);
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // FASTA + .fai (fai_fetch of a whole chromosome, R:...:87)
 // ------------------------------------------------------------------------------------------
@@ -383,27 +532,30 @@ void usage() {
                 "                                        included in per-base counts\n\n");
 }
 
-// samtools region string "name[:beg[-end]]"; returns 0 ok, -1 when only a name was given (beg/end untouched, A.6)
+// samtools region string "name[:beg[-end]]" as bam_parse_region (V:bam_aux.c:65-75) handles it.  Returns 0 when beg and end were
+// set; -1 when only the contig is known — a bare name, an open end ("chr:100", "chr:100-": the 64-bit end exceeds INT_MAX so the
+// legacy wrapper bails out after setting the contig) or unparsable coordinates: the caller's beg/end keep their previous values
+// (initially 0 .. 0x7fffffff; probe with the reference binary: "21:10405200" prints the whole contig, and as a second region it
+// repeats the previous one).  Thousands separators are accepted ("21:10,402,985-10,402,990").
 int parse_region(const BamFile &bam, const std::string &s, int &tid, int &beg, int &end) {
     std::string name = s; tid = -1;
-    size_t colon = s.rfind(':');
+    const size_t colon = s.rfind(':');
     bool ranged = false;
-    int64_t b = 0, e = 0x7fffffff;
+    int64_t b = 0, e = 0;
     if (colon != std::string::npos && bam.tid_of.find(s) == bam.tid_of.end()) {
         std::string coords = s.substr(colon + 1); name = s.substr(0, colon);
         coords.erase(std::remove(coords.begin(), coords.end(), ','), coords.end());
-        char *endp = nullptr;
-        b = std::strtoll(coords.c_str(), &endp, 10);
-        if (endp && *endp == '-') e = std::strtoll(endp + 1, nullptr, 10);
-        else if (endp && *endp == 0) e = 0x7fffffff;
-        b = b > 0 ? b - 1 : 0;
-        ranged = true;
+        const char *c = coords.c_str();
+        auto digits = [](const char *&q, int64_t &v) { const char *q0 = q; v = 0; while (*q >= '0' && *q <= '9') { v = v * 10 + (*q - '0'); ++q; } return q != q0; };
+        if (*c == '-') { ++c; b = 1; ranged = digits(c, e); }                     // "chr:-end": from the first base
+        else if (digits(c, b) && *c == '-') { ++c; ranged = digits(c, e); }       // "chr:beg-end"; "chr:beg" / "chr:beg-" stay open
+        if (ranged) b = b > 0 ? b - 1 : 0;
     }
     auto it = bam.tid_of.find(name);
     if (it == bam.tid_of.end()) return -1;
     tid = it->second;
-    if (!ranged) return -1;          // hts_parse_reg yields end = INT64_MAX -> bam_parse_region returns -1 after setting ref
-    beg = (int)b; end = (int)std::min<int64_t>(e, 0x7fffffff);
+    if (!ranged) return -1;
+    beg = (int)std::min<int64_t>(b, 0x7fffffff); end = (int)std::min<int64_t>(e, 0x7fffffff);
     return 0;
 }
 
@@ -432,18 +584,25 @@ int main(int argc, char **argv) {
     std::vector<std::string> region_args(argv + optind + 1, argv + argc);
     std::fprintf(stderr, "Minimum mapping quality is set to %d\n", min_mapq);
     if (dist_arg == "1" || dist_arg == "true") { std::fprintf(stderr, "Not currently supporting distributions\n"); return 1; }
-    (void)max_warn;
 
     // CUDA context creation takes a second or two: do it while the BAM header, index and FASTA index are read
     brc_config cfg{}; cfg.min_mapq = min_mapq; cfg.min_bq = min_bq; cfg.max_cnt = max_cnt; cfg.per_lib = per_lib; cfg.insertion_centric = ic;
     cfg.n_libs = 0; cfg.device = std::getenv("BRC_DEVICE") ? std::atoi(std::getenv("BRC_DEVICE")) : 0;
     const bool decode_only = std::getenv("BRC_CLI_DECODE_ONLY") != nullptr;   // test hook: exercise BGZF/BAI/region fetch without a GPU
     int warm_rc = BRC_OK;
-    std::thread warm([&] { if (decode_only) return; brc_config c0 = cfg; c0.per_lib = 0; brc_engine *tmp = nullptr; warm_rc = brc_create(&c0, &tmp); if (tmp) brc_destroy(tmp); });
+    brc_config warm_cfg = cfg; warm_cfg.per_lib = 0;
+    std::thread warm([&warm_rc, warm_cfg, decode_only] { if (decode_only) return; brc_engine *tmp = nullptr; warm_rc = brc_create(&warm_cfg, &tmp); if (tmp) brc_destroy(tmp); });
 
     BamFile bam;
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
-    if (bam_path.size() > 5 && bam_path.substr(bam_path.size() - 5) == ".cram") { std::fprintf(stderr, "CRAM input is not supported by this host; convert to BAM\n"); return 1; }
+    const bool is_cram = bam_path.size() > 5 && bam_path.substr(bam_path.size() - 5) == ".cram";
+#ifdef BRC_WITH_HTSLIB
+    HtsSource hts;
+    if (is_cram) { if (!hts.open(bam_path, fn_fa, bam)) { std::fprintf(stderr, "Fail to open BAM file %s\n", bam_path.c_str()); return 1; } }
+    else
+#else
+    if (is_cram) { std::fprintf(stderr, "CRAM input needs a host built with htslib (tools/build_htslib.sh, then python -m bam_readcount_b200.build); convert to BAM\n"); return 1; }
+#endif
     if (!bam.open(bam_path)) { std::fprintf(stderr, "Fail to open BAM file %s\n", bam_path.c_str()); return 1; }
     Fasta fa;
     const bool have_fa = !fn_fa.empty() && fa.open(fn_fa);
@@ -471,6 +630,10 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "Whole-file mode is not supported (the reference skips its per-read pre-processing there, R:...:624); give regions or -l\n");
         return 1;
     }
+#ifdef BRC_WITH_HTSLIB
+    if (is_cram) { if (!hts.load_index(bam_path)) { std::fprintf(stderr, "BAM indexing file is not available.\n"); return 1; } }
+    else
+#endif
     if (!bam.load_index(bam_path)) { std::fprintf(stderr, "BAM indexing file is not available.\n"); return 1; }
     if (!have_fa && !decode_only) { std::fprintf(stderr, "A reference FASTA (-f) is required in region / site-list mode\n"); return 1; }
 
@@ -480,7 +643,7 @@ int main(int argc, char **argv) {
     int rc = decode_only ? BRC_OK : (warm_rc != BRC_OK ? warm_rc : brc_create(&cfg, &eng));
     if (rc != BRC_OK) { std::fprintf(stderr, "brc_create: %s\n", brc_strerror(rc)); return 1; }
 
-    struct Region { int tid, beg, end; bool site_list; };
+    struct Region { int tid, beg, end; bool site_list; bool cont = false; };   // cont: a later window of a cut region (its halo site belongs to the window before)
     std::vector<Region> regions;
     if (!fn_pos.empty()) {
         std::ifstream fp(fn_pos);
@@ -516,7 +679,9 @@ int main(int argc, char **argv) {
             if (e_eff - g.beg <= W) { cut.push_back(g); continue; }
             for (int64_t b = g.beg; b < e_eff; b += W) {
                 const bool last = b + W >= e_eff;
-                cut.push_back({g.tid, (int)b, last ? g.end : (int)(b + W), last ? g.site_list : true});
+                Region w{g.tid, (int)b, last ? g.end : (int)(b + W), last ? g.site_list : true};
+                w.cont = b != g.beg;
+                cut.push_back(w);
             }
         }
         regions.swap(cut);
@@ -527,6 +692,8 @@ int main(int argc, char **argv) {
     const bool timing = std::getenv("BRC_CLI_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_decode = 0, t_compute = 0, t_format = 0, t_write = 0, t_ref = 0;
+    Warner warner(max_warn, min_mapq, min_bq, per_lib, ic);
+    int64_t warn_total[4] = {0, 0, 0, 0};
     auto flush = [&]() -> int {
         const double c0 = now();
         int r = brc_compute(eng);
@@ -549,9 +716,12 @@ int main(int argc, char **argv) {
                     if (brc_write_text(eng, g, first, WIN, lib_ptrs.data(), STDOUT_FILENO) < 0) { std::fprintf(stderr, "format: %s\n", brc_last_error(eng)); return -1; }
         }
         t_format += now() - f0;
+        { int64_t wc[4]; if (brc_get_warning_counts(eng, wc) == BRC_OK) for (int k = 0; k < 4; ++k) warn_total[k] += wc[k]; }
+        warner.replay();
         return brc_reset(eng);
     };
     int64_t pushed = 0;
+    if (eng) brc_set_queue_carry(eng, 1);    // argv regions are flushed batch by batch: their never-cleared deletion queue travels with the engine
     const double t_loop0 = now();
     RegionFetcher fetcher(bam);
     auto next_fbeg = [&](size_t gi) -> int64_t {   // start of the following fetch when it continues this one, else "keep nothing"
@@ -564,7 +734,11 @@ int main(int argc, char **argv) {
         if (decode_only) {
             const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
             int64_t n = 0, psum = 0, qsum = 0;
-            fetcher.fetch(g.tid, fbeg, fend, next_fbeg(gi), [&](const Rec &r) { ++n; psum += r.pos; for (int k = 0; k < r.l_qseq; ++k) qsum += r.qual[k]; });
+            auto count = [&](const Rec &r) { ++n; psum += r.pos; for (int k = 0; k < r.l_qseq; ++k) qsum += r.qual[k]; };
+#ifdef BRC_WITH_HTSLIB
+            if (is_cram) hts.fetch(g.tid, fbeg, fend, count); else
+#endif
+            fetcher.fetch(g.tid, fbeg, fend, next_fbeg(gi), count);
             std::printf("%d\t%d\t%d\t%lld\t%lld\t%lld\n", g.tid, g.beg, g.end, (long long)n, (long long)psum, (long long)qsum);
             continue;
         }
@@ -577,31 +751,43 @@ int main(int argc, char **argv) {
         }
         const double d1 = now();
         brc_begin_region(eng, g.tid, g.beg, g.end, g.site_list ? 1 : 0);
+        warner.begin_region(g.tid, g.beg, g.end, g.cont);
         // samfetch(in, idx, ref, d.beg-1, d.end): records with tid, endpos > max(beg-1,0), pos < end, in file order
         const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
         int push_rc = BRC_OK;
-        fetcher.fetch(g.tid, fbeg, fend, next_fbeg(gi), [&](const Rec &r) {
+        auto push = [&](const Rec &r) {
             uint16_t lib = 0;
             if (per_lib) {
                 lib = (uint16_t)BRC_LIB_NONE;
                 if (r.has_rg) { auto it = rg_lb.find(r.rg); if (it != rg_lb.end()) lib = lib_rank[it->second]; }
             }
+            warner.consider(r, lib == (uint16_t)BRC_LIB_NONE);
             const int prc = brc_push_read(eng, r.tid, r.pos, r.flag, r.mapq, lib, r.l_qseq, r.nm, r.sm, r.n_cigar, r.cigar, r.seq, r.qual);
             if (prc != BRC_OK && push_rc == BRC_OK) push_rc = prc;
             ++pushed;
-        });
+        };
+#ifdef BRC_WITH_HTSLIB
+        if (is_cram) hts.fetch(g.tid, fbeg, fend, push); else
+#endif
+        fetcher.fetch(g.tid, fbeg, fend, next_fbeg(gi), push);
         if (push_rc != BRC_OK) { std::fprintf(stderr, "brc_push_read: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
         brc_end_region(eng);
         t_decode += now() - d1;
-        // site-list regions are independent: flush in batches; argv regions share the deletion queue -> one batch
-        const bool next_is_argv_chain = gi + 1 < regions.size() && !g.site_list;     // argv regions share the deletion queue: keep them in one batch
-        if (gi + 1 == regions.size() || (!next_is_argv_chain && pushed > 1500000)) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
+        // flush in batches at region boundaries; the deletion queue of the argv loop is carried by the engine (brc_set_queue_carry)
+        if (gi + 1 == regions.size() || pushed > 1500000) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
     }
+    warner.finish(warn_total);
+#ifdef BRC_WITH_HTSLIB
+    const bool decode_error = bam.bz.error || hts.error;
+#else
+    const bool decode_error = bam.bz.error;
+#endif
+    if (decode_error) std::fprintf(stderr, "[E::bgzf_read] %s: truncated or corrupt BGZF block / BAM record — the output above is incomplete\n", bam_path.c_str());
     if (timing) std::fprintf(stderr, "[brc timing] index seeks %llu  records decoded %llu\n", (unsigned long long)fetcher.n_seeks, (unsigned long long)fetcher.n_decoded);
-    if (decode_only) return 0;
+    if (decode_only) return decode_error ? 1 : 0;
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
     const double t_d0 = now();
     brc_destroy(eng);
     if (timing) std::fprintf(stderr, "[brc timing] startup (CUDA context, header, index) %.3fs  teardown %.3fs\n", t_loop0 - t_main0, now() - t_d0);
-    return 0;
+    return decode_error ? 1 : 0;
 }

@@ -28,6 +28,8 @@ constexpr uint32_t FM_SIMPLE = 1u << 24;     // CIGAR has exactly one ref-consum
 constexpr uint32_t FM_NM_ABSENT = 1u << 25;  // NM tag missing -> NM_TAG_MISSING warning per process_read
 constexpr uint32_t FM_SM_MISSING = 1u << 26; // proper pair without SM tag -> SM_TAG_MISSING warning per process_read
 constexpr uint32_t FM_FASTDIV = 1u << 27;    // 1 <= l_qseq, clipped_length <= FASTDIV_MAX: reciprocal division is exact (tests)
+constexpr uint32_t FM_HOT = 1u << 28;        // SIMPLE && FASTDIV && no missing-tag warnings: the hot loop's straight-line path
+constexpr uint32_t FM_DEAD = 1u << 29;       // fails -q or the flag filter (R:bamreadcount.cpp:288-310): only counts as a spanning read
 constexpr int FASTDIV_MAX = 2048;
 
 struct __align__(16) ReadDesc {
@@ -55,7 +57,7 @@ struct __align__(16) ReadDesc {
     float rcp_l;        // RN(1 / (float)l_qseq)         (FM_FASTDIV only)
     float rcp_clen;     // RN(1 / (float)clipped_length) (FM_FASTDIV only)
     float fclen;        // (float)clipped_length
-    uint32_t pad1;
+    uint32_t inc;       // per-event increments of the packed chunk counters: 1 | plus << 8 | (q2 > -1) << 16
 };
 static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
 
@@ -66,6 +68,7 @@ static_assert(sizeof(ReadDesc) == 80, "ReadDesc must be 80 bytes");
 constexpr int STAGE_READS = BRC_STAGE_READS;                 // descriptors per chunk
 constexpr int STAGE_QUAL = STAGE_READS * 152 + 32;          // staged quality bytes per chunk (incl. 16-B alignment slack both ends)
 constexpr int STAGE_SEQ = STAGE_READS * 76 + 32;            // staged packed-base bytes per chunk
+constexpr int STAGE_CIGAR = STAGE_READS * 2;                // staged CIGAR ops per chunk (u32); chunks with more fall back to global loads
 
 struct TileInfo {
     int32_t pos0;       // absolute position of the tile's first site
@@ -145,6 +148,7 @@ struct ResultsDev {
 struct PileupParams {
     int32_t min_mapq, min_bq, per_lib, insertion_centric;
     const ReadDesc *desc;
+    const uint64_t *cigar_off; // [n_reads+1]
     const uint32_t *cigar;
     const uint8_t *seq;       // 16-byte aligned, >= 16 readable bytes past the last read
     const uint8_t *qual;      // 16-byte aligned, >= 16 readable bytes past the last read
@@ -186,6 +190,7 @@ struct PrecomputeParams {
     int32_t *tile_hi;
     int64_t read_begin;    // this launch covers reads [read_begin, read_end)
     int64_t read_end;
+    int32_t min_mapq;      // -q: reads below it (or failing the flag filter) are marked FM_DEAD
 };
 
 // launch wrappers (brc_kernels.cu)

@@ -129,15 +129,12 @@ int brc_set_reference_device(brc_engine *e, int32_t tid, const char *contig_name
     cudaStream_t s = (cudaStream_t)stream;
     HostRef *r = nullptr;
     for (auto &x : e->refs) if (x.tid == tid) r = &x;
-    const bool is_new = r == nullptr;
     if (!r) { e->refs.emplace_back(); r = &e->refs.back(); }
-    const void *old_ptr = r->dev.p;
     r->tid = tid; r->name = contig_name ? contig_name : ""; r->chrom_len = chrom_len; r->win_beg = win_beg; r->win_len = win_len;
     r->seq.clear();
     CU(r->dev.reserve((size_t)win_len / 2 + 32), "cudaMalloc(reference)");
     CU(cudaMemsetAsync(r->dev.p, 0xFF, (size_t)win_len / 2 + 32, s), "memset(reference)");
     CU(launch_ref_encode(dev_ascii, r->dev.as<uint8_t>(), win_len, s), "reference encode");
-    (void)is_new; (void)old_ptr;
     std::vector<RefWin> tab(e->refs.size());
     for (size_t i = 0; i < e->refs.size(); ++i)
         tab[i] = RefWin{e->refs[i].dev.as<char>(), e->refs[i].chrom_len, e->refs[i].win_beg, e->refs[i].win_len};
@@ -422,10 +419,10 @@ static void make_params(brc_engine *e, const int32_t *d_region_of_read, Precompu
     P0.reads = e->dev_reads; P0.regions = e->d_regions.as<RegionDev>(); P0.n_regions = (int64_t)e->regions_dev.size();
     P0.region_of_read = d_region_of_read; P0.refs = e->d_refs.as<RefWin>(); P0.desc = e->d_desc.as<ReadDesc>();
     P0.tile_lo = e->d_tile_lo.as<int32_t>(); P0.tile_hi = e->d_tile_hi.as<int32_t>();
-    P0.read_begin = 0; P0.read_end = e->dev_reads.n_reads;
+    P0.read_begin = 0; P0.read_end = e->dev_reads.n_reads; P0.min_mapq = e->cfg.min_mapq;
     P1 = PileupParams{};
     P1.min_mapq = e->cfg.min_mapq; P1.min_bq = e->cfg.min_bq; P1.per_lib = e->cfg.per_lib; P1.insertion_centric = e->cfg.insertion_centric;
-    P1.desc = e->d_desc.as<ReadDesc>(); P1.cigar = e->dev_reads.cigar; P1.seq = e->dev_reads.seq; P1.qual = e->dev_reads.qual;
+    P1.desc = e->d_desc.as<ReadDesc>(); P1.cigar_off = e->dev_reads.cigar_off; P1.cigar = e->dev_reads.cigar; P1.seq = e->dev_reads.seq; P1.qual = e->dev_reads.qual;
     P1.seq_off = e->dev_reads.seq_off; P1.qual_off = e->dev_reads.qual_off;
     P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size(); P1.tile_begin = 0; P1.tile_count = P1.n_tiles;
     P1.res = results_dev(e);

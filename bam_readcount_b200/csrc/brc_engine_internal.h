@@ -1,6 +1,8 @@
 // brc_engine_internal.h — host-side engine state shared by brc_engine.cu and brc_format.cpp.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <deque>
 #include <queue>
 #include <string>
 #include <vector>
@@ -69,6 +71,18 @@ struct Admission {
     void reset() { it_tid = 0; it_pos = 0; max_tid = -1; max_pos = -1; live_ends = decltype(live_ends)(); }
 };
 
+// IndelQueue state of the text emitter (R:src/lib/bamrc/IndelQueue.cpp:3-15): per library row, the deletions waiting for the
+// line of the site after their anchor.  The argv-region loop of the reference never clears it (R:bamreadcount.cpp:650-656).
+struct QEnt { int32_t tid; int64_t pos; uint32_t st[BRC_N_STATS]; std::string allele; };
+struct EmitState {
+    std::vector<std::deque<QEnt>> q;
+    std::vector<char> q_exists;
+    EmitState() {}
+    explicit EmitState(int rows) : q((size_t)rows), q_exists((size_t)rows, 0) {}
+    void clear() { for (auto &d : q) d.clear(); std::fill(q_exists.begin(), q_exists.end(), 0); }
+    bool pending() const { for (auto &d : q) if (!d.empty()) return true; return false; }
+};
+
 }  // namespace brc
 
 struct brc_engine {
@@ -131,6 +145,11 @@ struct brc_engine {
 
     // text of the last brc_format_* call, so the usual size-query + fill pair formats only once
     std::vector<std::string> fmt_parts; int64_t fmt_key[3] = {-2, -2, -2}; bool fmt_valid = false;
+
+    // deletion queue carried from one formatting pass to the next (brc_set_queue_carry): lets a caller flush argv regions
+    // batch by batch and still reproduce the reference's never-cleared queue
+    bool carry_on = false;
+    brc::EmitState carry;
 
     int launch_count = 0;
 };

@@ -53,13 +53,12 @@ void put_stat(std::string &o, const Stat *s, bool is_indel) {
     put_f2(o, f32(v[BRC_S_3P_DIST]) / rc);
 }
 
-struct QEnt { int32_t tid; int64_t pos; Stat st; std::string allele; };
-struct EmitState {
-    std::vector<std::deque<QEnt>> q;
-    std::vector<char> q_exists;
-    explicit EmitState(int rows) : q((size_t)rows), q_exists((size_t)rows, 0) {}
-    void clear() { for (auto &d : q) d.clear(); std::fill(q_exists.begin(), q_exists.end(), 0); }
-};
+using brc::QEnt;
+using brc::EmitState;
+inline QEnt make_qent(int32_t tid, int64_t pos, const Stat &st, const std::string &allele) {
+    QEnt q; q.tid = tid; q.pos = pos; std::memcpy(q.st, st.v, sizeof q.st); q.allele = allele; return q;
+}
+inline const Stat *qstat(const QEnt &q) { return reinterpret_cast<const Stat *>(q.st); }
 
 const char kNt[] = "=ACGTN";
 const uint8_t kCanon[16] = {0, 1, 2, 5, 3, 5, 5, 5, 4, 5, 5, 5, 5, 5, 5, 5};
@@ -122,15 +121,15 @@ void format_site(const View &V, int32_t s, const char *const *lib_names, EmitSta
         if (emit) for (int j = 0; j < 6; ++j) { rec += '\t'; rec += kNt[j]; rec += ':'; put_stat(rec, have[j] ? &base[j] : nullptr, false); }
         if (W.indels.size() > 1) std::sort(W.indels.begin(), W.indels.end(), [](const Indel &a, const Indel &b) { return a.allele < b.allele; });
         for (auto &in : W.indels) {
-            if (in.allele[0] == '-') { st.q[(size_t)r].push_back(QEnt{rg.tid, pos + 1, in.st, in.allele}); st.q_exists[(size_t)r] = 1; }
+            if (in.allele[0] == '-') { st.q[(size_t)r].push_back(make_qent(rg.tid, pos + 1, in.st, in.allele)); st.q_exists[(size_t)r] = 1; }
             else if (emit) { rec += '\t'; rec += in.allele; rec += ':'; put_stat(rec, &in.st, true); }
         }
         if (emit && st.q_exists[(size_t)r]) {          // IndelQueue::process(tid, pos, record)
             auto &q = st.q[(size_t)r];
             while (!q.empty() && ((q.front().tid == rg.tid && q.front().pos < pos) || q.front().tid != rg.tid)) q.pop_front();
             while (!q.empty() && q.front().tid == rg.tid && q.front().pos == pos) {
-                rec += '\t'; rec += q.front().allele; rec += ':'; put_stat(rec, &q.front().st, true);
-                extra_depth += q.front().st.v[BRC_S_COUNT];
+                rec += '\t'; rec += q.front().allele; rec += ':'; put_stat(rec, qstat(q.front()), true);
+                extra_depth += q.front().st[BRC_S_COUNT];
                 q.pop_front();
             }
         }
@@ -166,6 +165,7 @@ void format_region(const brc_engine *e, int64_t g, int32_t s0, int32_t s1, const
     // The deletion queue carries state across sites.  Inside one region only the site to the left matters, so ranges can be
     // formatted independently — except in the argv loop with several regions, whose queue is never cleared (A.6): keep that sequential.
     if (!rg.site_list_mode && e->regions.size() > 1) nt = 1;
+    if (st.pending()) nt = 1;      // entries carried in from an earlier region / batch may print anywhere in this range
     const size_t base = parts_out.size();
     parts_out.resize(base + (size_t)nt);
     if (nt <= 1) {
@@ -232,12 +232,20 @@ void ensure_formatted(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const c
     if (e->fmt_valid && e->fmt_key[0] == k0 && e->fmt_key[1] == k1 && e->fmt_key[2] == k2) return;
     brc::ensure_wide(e);
     e->fmt_parts.clear();
-    EmitState st(e->n_rows);
+    // deletion queue: fresh per call, or (brc_set_queue_carry) the one the previous formatting pass left behind
+    const bool carry = e->carry_on && (k1 == -1 || k1 == 0);
+    if (e->carry.q.size() != (size_t)e->n_rows) e->carry = EmitState(e->n_rows);
+    EmitState local(e->n_rows);
+    EmitState &st = carry ? e->carry : local;
     if (k1 == -1) {   // whole regions
         if (k0 < 0 && !format_many_site_list_regions(e, lib_names, e->fmt_parts))
             for (int64_t g = 0; g < (int64_t)e->regions.size(); ++g) format_region(e, g, 0, e->regions[(size_t)g].n_slots, lib_names, st, e->fmt_parts, false);
         if (k0 >= 0) format_region(e, k0, 0, e->regions[(size_t)k0].n_slots, lib_names, st, e->fmt_parts, false);
-    } else format_region(e, k0, (int32_t)k1, (int32_t)std::min<int64_t>(k1 + k2, 0x7fffffff), lib_names, st, e->fmt_parts, true);
+    } else {
+        format_region(e, k0, (int32_t)k1, (int32_t)std::min<int64_t>(k1 + k2, 0x7fffffff), lib_names, st, e->fmt_parts, !carry);
+        // a later window of a carried region: hand its final queue on when it reaches the region's end
+        if (e->carry_on && !carry && k1 + k2 >= e->regions[(size_t)k0].n_slots) e->carry = local;
+    }
     e->fmt_key[0] = k0; e->fmt_key[1] = k1; e->fmt_key[2] = k2; e->fmt_valid = true;
 }
 int64_t parts_size(const brc_engine *e) { int64_t n = 0; for (auto &p : e->fmt_parts) n += (int64_t)p.size(); return n; }
@@ -266,6 +274,14 @@ int64_t serve(brc_engine *e, int64_t k0, int64_t k1, int64_t k2, const char *con
 }
 
 }  // namespace
+
+extern "C" int brc_set_queue_carry(brc_engine *e, int on) {
+    if (!e) return BRC_E_INVALID;
+    e->carry_on = on != 0;
+    e->carry = EmitState(e->n_rows);
+    e->fmt_valid = false;
+    return BRC_OK;
+}
 
 extern "C" int64_t brc_format_text(brc_engine *e, int64_t region_index, const char *const *lib_names, char *buf, int64_t cap) {
     if (!e) return BRC_E_INVALID;

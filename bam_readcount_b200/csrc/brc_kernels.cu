@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     else se = (int32_t)mapq;
     const bool fast = l_qseq >= 1 && l_qseq <= FASTDIV_MAX && clipped_length >= 1 && clipped_length <= FASTDIV_MAX;
     if (fast) fm |= FM_FASTDIV;
+    if (simple && fast && !(fm & (FM_NM_ABSENT | FM_SM_MISSING))) fm |= FM_HOT;
+    if ((int)mapq < P.min_mapq || (flag & FLAG_FILTER)) fm |= FM_DEAD;
     d.fm = fm;
     d.mmq = (int32_t)sum_mmq; d.clen = clipped_length; d.lclip = left_clip; d.tpi = tpi;
     d.q2 = q2_pos;
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(K0_READS) read_precompute_kernel(PrecomputePar
     d.cig = simple ? (uint32_t)qoff : (uint32_t)coff; d.n_cigar = n_cigar;
     d.rcp_l = fast ? __frcp_rn((float)l_qseq) : 0.0f;
     d.rcp_clen = fast ? __frcp_rn((float)clipped_length) : 0.0f;
-    d.fclen = (float)clipped_length; d.pad1 = 0;
+    d.fclen = (float)clipped_length; d.inc = 1u | ((flag & 16u) ? 0u : 256u) | (q2_pos > -1 ? 65536u : 0u);
     // 5 x 16-byte stores
     int4 *dst = reinterpret_cast<int4 *>(P.desc + i);
     const int4 *src = reinterpret_cast<const int4 *>(&d);
@@ -604,15 +606,17 @@ struct __align__(16) ChunkInfo {
     int32_t work;        // work item (row * n_tiles + tile), -1 = no more work
     int32_t r0, r1;      // reads [r0, r1) staged in this slot
     uint32_t qbase32, sbase32;
-    uint32_t flags;      // bit0 staged (qual/seq in smem), bit1 first chunk of the tile, bit2 last chunk of the tile
+    uint32_t flags;      // bit0 staged (qual/seq in smem), bit1 first chunk of the tile, bit2 last chunk of the tile, bit3 narrow -p tile,
+                         // bit4 CIGAR ops staged (cbase32 = index of the first staged op)
     int32_t pos0, n;     // TileInfo
     int64_t slot0;
-    uint32_t row, pad;
+    uint32_t row, cbase32;
 };
 struct __align__(128) StageBuf {
     int4 desc[STAGE_READS * 5];
     uint8_t qual[STAGE_QUAL];
     uint8_t seq[STAGE_SEQ];
+    uint32_t cigar[STAGE_CIGAR];
 };
 struct __align__(128) PileupSmem {
     StageBuf st[NSTAGE];
@@ -667,6 +671,12 @@ __device__ __forceinline__ uint32_t slot_index(const PileupParams &P, const Chun
 }
 
 // The hot loop: one warp walks the chunk's reads in file order; lane = site.
+//
+// K0 has already classified every read (uniform per iteration): FM_DEAD reads only count as spanning reads; FM_HOT reads
+// (one match-type CIGAR op, lengths <= FASTDIV_MAX, no missing tag) take a straight-line path whose event is the site's
+// primary base class in ~99 % of the cases; everything else takes the general path.  The primary class's small integer
+// sums are kept PACKED for the duration of a chunk (<= STAGE_READS events per lane: three 8-bit counters in one word,
+// two 16-bit sums in another) and flushed into the full-width accumulators at the end of the chunk.
 template <bool PER_LIB, bool STAGED>
 __device__ __forceinline__ void process_chunk(const PileupParams &P, const StageBuf &sb, uint32_t (*sacc)[TILE], uint32_t (*warn)[TILE],
                                               const ChunkInfo &ci, SiteState &S, int tid) {
@@ -688,10 +698,17 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         if (start >= n_in) return;
         ds += start * 5;
     }
+    uint32_t pk3 = 0u, pkmb = 0u;                                 // count | plus << 8 | nq2 << 16 ;  baseq | mapq << 16
+#ifndef BRC_K1_NO_PREFETCH
     int2 pe_next = lds_i2(ds);                                    // software prefetch of the next read's (pos,end)
+#endif
     for (; ds < ds_end; ds += 5) {
+#ifndef BRC_K1_NO_PREFETCH
         const int2 pe = pe_next;
         pe_next = lds_i2(ds + 5);                                 // may run one record past the chunk: staged garbage, never used
+#else
+        const int2 pe = lds_i2(ds);
+#endif
         if (pe.x > wlast) { S.warp_done = true; break; }          // reads are position-sorted within a region
         if (pe.y <= wfirst) continue;
         const bool cover = S.site >= pe.x && S.site < pe.y;
@@ -709,33 +726,69 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         const uint32_t fm = (uint32_t)fl2.x;
         const int4 q3 = ds[3];                                   // qual32,seq32,cig,n_cigar
         int qpos, indel = 0;
-        if (fm & FM_SIMPLE) qpos = S.site - pe.x + q3.z;
-        else {
-            const int3 rr = resolve_general(P.cigar + (uint32_t)q3.z, (uint32_t)q3.w, pe.x, S.site);
-            if (rr.z) continue;                                  // is_del
-            qpos = rr.x; indel = rr.y;
-        }
-        const uint32_t mapq = (fm >> 16) & 0xFFu;
-        if ((int)mapq < P.min_mapq) continue;
-        uint32_t bq;
-        if (STAGED) bq = lds_u8(qual_s + (uint32_t)q3.x + (uint32_t)qpos);
-        else bq = P.qual[P.qual_off[ci.r0 + (int)((ds - sb.desc) / 5)] + (uint32_t)qpos];
-        if ((int)bq < P.min_bq) continue;
-        if (fm & FLAG_FILTER) continue;
-        S.npass++;
-        const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // a tag the reference warns about is missing
-        if (indel != 0) {
-            const int32_t r = ci.r0 + (int)((ds - sb.desc) / 5);
-            S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
+        uint32_t bq, base;
+        if (fm & FM_HOT) {
+            // ---- straight-line path: filters decided by K0, single match op, exact reciprocal divisions ----
+            if (fm & FM_DEAD) continue;
+            qpos = S.site - pe.x + q3.z;
+            if (STAGED) bq = lds_u8(qual_s + (uint32_t)q3.x + (uint32_t)qpos);
+            else bq = P.qual[P.qual_off[ci.r0 + (int)((ds - sb.desc) / 5)] + (uint32_t)qpos];
+            if ((int)bq < P.min_bq) continue;
+            S.npass++;
+            uint32_t byte;
+            if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
+            else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
+            base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
+            if (S.pbase == NO_BASE) S.pbase = base;
+            if (base == S.pbase) {
+                const int4 q1 = ds[1];                           // mmq,clen,lclip,tpi
+                const int4 q2 = ds[2];                           // q2,nmfrac,se,fl
+                const int4 q4 = ds[4];                           // rcp_l, rcp_clen, fclen, inc
+                const float fl = __int_as_float(q2.w), rcp_l = __int_as_float(q4.x);
+                const float d3 = div_small((float)abs(qpos - q1.w), fl, rcp_l);
+                const float f = div_small((float)abs(2 * (qpos - q1.z) - q1.y), __int_as_float(q4.z), __int_as_float(q4.y));
+                Acc &a = S.acc;
+                pk3 += (uint32_t)q4.w;
+                pkmb += (fm & 0x00FF0000u) + bq;
+                a.mmqs += (uint32_t)q1.x; a.clip += (uint32_t)q1.y; a.se += (uint32_t)q2.z;
+                if (q4.w & 0x10000) {                            // the read has a Q2 position (usually == the effective 3' end, R:...:229-238)
+                    const float q2t = q2.x == q1.w ? d3 : div_small((float)abs(qpos - q2.x), fl, rcp_l);
+                    a.q2d = __fadd_rn(a.q2d, q2t);
+                }
+                a.d3p = __fadd_rn(a.d3p, d3);
+                a.posd = round_to_f32_precision(__dadd_rn(a.posd, __dsub_rn(1.0, f32_to_f64_nonneg(f))));
+                a.nmf = __fadd_rn(a.nmf, __int_as_float(q2.y));
+                continue;
+            }
+        } else {
+            // ---- general path ----
+            if (fm & FM_SIMPLE) qpos = S.site - pe.x + q3.z;
+            else {
+                const uint32_t *cig_base = (ci.flags & 16u) ? sb.cigar - ci.cbase32 : P.cigar;   // staged ops are indexed with the reads' pool op indices
+                const int3 rr = resolve_general(cig_base + (uint32_t)q3.z, (uint32_t)q3.w, pe.x, S.site);
+                if (rr.z) continue;                              // is_del
+                qpos = rr.x; indel = rr.y;
+            }
+            if (fm & FM_DEAD) continue;                          // mapq / flag filter (R:...:288-310)
+            if (STAGED) bq = lds_u8(qual_s + (uint32_t)q3.x + (uint32_t)qpos);
+            else bq = P.qual[P.qual_off[ci.r0 + (int)((ds - sb.desc) / 5)] + (uint32_t)qpos];
+            if ((int)bq < P.min_bq) continue;
+            S.npass++;
+            const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // a tag the reference warns about is missing
+            if (indel != 0) {
+                const int32_t r = ci.r0 + (int)((ds - sb.desc) / 5);
+                S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
+                if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
+                if (indel > 0 && P.insertion_centric) continue;
+            }
             if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
-            if (indel > 0 && P.insertion_centric) continue;
+            uint32_t byte;
+            if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
+            else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
+            base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
+            if (S.pbase == NO_BASE) S.pbase = base;
         }
-        if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
-        uint32_t byte;
-        if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
-        else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
-        const uint32_t base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
-        if (S.pbase == NO_BASE) S.pbase = base;
+        // ---- an event that is not (hot, primary): full-width accumulation ----
         if (base != S.pbase && S.sbase != NO_BASE && base != S.sbase) {   // third base class at this site: rare
             S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), (int)base, 0, ci.r0 + (int)((ds - sb.desc) / 5), qpos, bq, false);
             continue;
@@ -747,6 +800,7 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
                                     __int_as_float(q4.x), __int_as_float(q4.y));
         const bool has_q2 = q2.x > -1;
         const uint32_t plus = (fm & 16u) ? 0u : 1u;
+        const uint32_t mapq = (fm >> 16) & 0xFFu;
         const float nmterm = __int_as_float(q2.y);
         if (base == S.pbase) {
             Acc &a = S.acc;
@@ -774,6 +828,9 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
             sacc[12][tid] = __float_as_uint(__fadd_rn(__uint_as_float(sacc[12][tid]), t.d3pterm));
         }
     }
+    // flush the chunk's packed counters of the primary class
+    S.acc.count += pk3 & 0xFFu; S.acc.plus += (pk3 >> 8) & 0xFFu; S.acc.nq2 += pk3 >> 16;
+    S.acc.baseq += pkmb & 0xFFFFu; S.acc.mapq += pkmb >> 16;
 }
 
 // Packs one site's header + primary accumulators into the 8-word narrow record, or escapes it to a full-width pool record
@@ -891,9 +948,12 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
                     }
                     const uint32_t db = (uint32_t)(r1 - r0) * (uint32_t)sizeof(ReadDesc);
                     const uint32_t qbytes = staged ? (uint32_t)(qb - qa) : 0u, sbytes = staged ? (uint32_t)(sb - sa) : 0u;
-                    bytes = db + qbytes + sbytes;
-                    ci.qbase32 = (uint32_t)qa; ci.sbase32 = (uint32_t)sa;
-                    ci.flags = staged ? 1u : 0u;
+                    // the chunk's CIGAR ops (contiguous in the pool), 16-byte aligned window of u32 ops
+                    const uint64_t ca = P.cigar_off[r0] & ~3ull, cb = (P.cigar_off[r1] + 3ull) & ~3ull;
+                    const uint32_t cbytes = (cb - ca) <= (uint64_t)STAGE_CIGAR ? (uint32_t)(cb - ca) * 4u : 0u;
+                    bytes = db + qbytes + sbytes + cbytes;
+                    ci.qbase32 = (uint32_t)qa; ci.sbase32 = (uint32_t)sa; ci.cbase32 = (uint32_t)ca;
+                    ci.flags = (staged ? 1u : 0u) | (cbytes ? 16u : 0u);
                     ci.r0 = r0; ci.r1 = r1;
                     ci.flags |= (first ? 2u : 0u) | (r1 >= hi ? 4u : 0u) | (narrow ? 8u : 0u);
                     sm.info[s] = ci;
@@ -901,6 +961,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
                     tma_bulk_g2s(sm.st[s].desc, P.desc + r0, db, &sm.full[s]);
                     if (qbytes) tma_bulk_g2s(sm.st[s].qual, P.qual + qa, qbytes, &sm.full[s]);
                     if (sbytes) tma_bulk_g2s(sm.st[s].seq, P.seq + sa, sbytes, &sm.full[s]);
+                    if (cbytes) tma_bulk_g2s(sm.st[s].cigar, P.cigar + ca, cbytes, &sm.full[s]);
                 } else {   // tile without reads, or the terminator
                     ci.r0 = ci.r1 = 0; ci.flags = 2u | 4u | (narrow ? 8u : 0u);
                     sm.info[s] = ci;

@@ -76,7 +76,7 @@ SEC_RECORD_BYTES = 72
 EXPORTS = [
     "brc_abi_version", "brc_create", "brc_destroy", "brc_last_error", "brc_strerror", "brc_set_reference", "brc_set_reference_device", "brc_reset",
     "brc_begin_region", "brc_push_read", "brc_push_reads", "brc_end_region", "brc_compute", "brc_get_results",
-    "brc_get_warning_counts", "brc_format_text", "brc_format_window", "brc_write_text", "brc_plan_device", "brc_run_device", "brc_device_packed_results", "brc_get_packed_results",
+    "brc_get_warning_counts", "brc_format_text", "brc_format_window", "brc_write_text", "brc_set_queue_carry", "brc_plan_device", "brc_run_device", "brc_device_packed_results", "brc_get_packed_results",
     "brc_fetch_device_results", "brc_last_launch_count", "brc_last_stage_ms", "brc_selftest_fastmath",
 ]
 
@@ -117,6 +117,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.brc_format_window.restype = C.c_int64
     lib.brc_write_text.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_char_p), C.c_int]
     lib.brc_write_text.restype = C.c_int64
+    lib.brc_set_queue_carry.argtypes = [C.c_void_p, C.c_int]
     lib.brc_plan_device.argtypes = [C.c_void_p, C.POINTER(CRegion), C.c_int64, C.c_int64, C.c_int64]
     lib.brc_run_device.argtypes = [C.c_void_p, C.POINTER(CReadBatch), C.c_void_p, C.c_void_p]
     lib.brc_device_packed_results.argtypes = [C.c_void_p, C.POINTER(CPackedResults)]

@@ -412,6 +412,7 @@ def run_wgs(args, cfg_name):
             if k < len(my_windows):
                 if resident and runners[0].window is not None:
                     r0 = runners[0]
+                    r0.stream.wait_event(r0.sent)                                           # the previous step's records have left the handle
                     r0.eng.run_device(r0.dw.c_batch(), None, r0.stream.cuda_stream)       # inputs stay resident: kernels only
                     with torch.cuda.stream(r0.stream):
                         r0.done.record(r0.stream)
@@ -448,7 +449,6 @@ def run_wgs(args, cfg_name):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    launches0 = 0
     for _ in range(args.steps):
         one_pass()
     join_streams()

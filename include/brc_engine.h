@@ -242,6 +242,13 @@ BRC_API int brc_get_warning_counts(brc_engine *e, int64_t out[4]);
  * Returns the number of bytes required (excluding NUL); writes at most cap-1 bytes + NUL. */
 BRC_API int64_t brc_format_text(brc_engine *e, int64_t region_index, const char *const *lib_names, char *buf, int64_t cap);
 
+/* The deletion queue of the reference's argv-region loop is never cleared between regions (R:bamreadcount.cpp:650-656; its -l
+ * loop clears it per line, :605).  By default every brc_format_* / brc_write_text call starts with an empty queue, so all argv
+ * regions of a run must be formatted in one call.  With carry ON the queue left by one formatting pass (all regions, or the
+ * windows of one region in order) is the starting queue of the next — across brc_reset / brc_compute — so a caller can flush
+ * argv regions batch by batch.  Switching it (on or off) empties the queue. */
+BRC_API int brc_set_queue_carry(brc_engine *e, int on);
+
 /* Same, for a window of one region's sites: slot offsets [first, first+count) inside region `region_index` (site
  * first_pos+first onwards).  Lets a caller stream the text of a large region piecewise; the window's first site
  * re-derives its deletion columns from the site to its left.  Formatting runs on several host threads. */

@@ -254,3 +254,161 @@ def test_cli_fetch_merging_two_contigs_unsorted_and_past_the_end(tmp_path):
         idx = both.fetch(tid, max(s - 2, 0), e)
         want = (tid, s - 1, e, len(idx), int(both.pos[idx].astype(np.int64).sum()), int(sum(int(both.qual[qo[i]:qo[i + 1]].astype(np.int64).sum()) for i in idx)))
         assert g == want, (c, s, e)
+
+
+# ---- the boundary compiled INTO the reference: its own main(), option parsing, htslib readers and region loops, with
+# ---- fetch_func / pileup_func / the pileup buffer replaced by the C ABI (oracle/patch_reference.py)
+def _patched_reference():
+    exe = os.path.join(ROOT, "oracle", "_ref", "bam-readcount-brc")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/bam-readcount-brc not built (oracle/build_patched_ref.sh, needs /root/reference)")
+    return exe
+
+
+def test_patched_reference_needs_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = _patched_reference()
+    data = os.path.join(ROOT, "oracle", "_ref", "test-data")
+    p = subprocess.run([exe, "-w", "1", "-f", "ref.fa", "-l", "site_list", "test.bam"], cwd=data, capture_output=True)
+    assert p.returncode == 1 and b"no usable CUDA device" in p.stderr and p.stdout == b""      # no CPU fallback behind the boundary
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,bam,golden", [
+    (["-w", "1", "-l", "site_list"], "test.bam", "expected_all_lib"),
+    (["-w", "1", "-p", "-l", "site_list"], "test.bam", "expected_per_lib"),
+    (["-w", "1", "-i", "-l", "site_list"], "test.bam", "expected_insertion_centric_all_lib"),
+    (["-w", "1", "-i", "-p", "-l", "site_list"], "test.bam", "expected_insertion_centric_per_lib"),
+    (["-w", "1", "REGIONS"], "test.bam", "expected_all_lib"),
+    (["-w", "1", "REGIONS"], "test_bad_rg.bam", "expected_all_lib"),
+])
+def test_reference_main_through_the_c_abi_reproduces_goldens(args, bam, golden):
+    """R:integration-test/bam-readcount_test.py:29-116 — the six command lines, run by the reference's own main()
+    linked against libbrc_engine.so."""
+    exe = _patched_reference()
+    data = os.path.join(ROOT, "oracle", "_ref", "test-data")
+    argv = [exe, "-f", "ref.fa"]
+    regions = []
+    for a in args:
+        if a == "REGIONS":
+            regions = ["21:10402985-10402985", "21:10405200-10405200"]
+        else:
+            argv.append(a)
+    argv.append(bam)
+    argv += regions
+    p = subprocess.run(argv, cwd=data, capture_output=True)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout.decode("latin-1") == cases.load_golden_text(golden)
+
+
+@pytest.mark.gpu
+def test_reference_main_through_the_c_abi_on_the_cram():
+    """BASELINE config 2b on the CRAM itself: htslib (the reference's reader) decodes twolib.sorted.cram, the engine computes."""
+    exe = _patched_reference()
+    data = os.path.join(ROOT, "oracle", "_ref", "test-data")
+    for extra, golden in ((["-p"], "ref_cram_twolib_perlib.txt"), ([], "ref_cram_twolib_alllib.txt")):
+        p = subprocess.run([exe, "-w", "0"] + extra + ["-f", "rand1k.fa", "-l", "twolib_site_list.txt", "twolib.sorted.cram"], cwd=data, capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+        assert p.stdout.decode("latin-1") == cases.load_golden_text(golden)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args,bam", [
+    (["-w", "3", "-l", "site_list"], "test.bam"),
+    (["-w", "2", "-p", "-l", "site_list"], "test_bad_rg.bam"),
+    (["-w", "5", "-i", "REGION"], "test.bam"),
+    (["-w", "0", "-l", "site_list"], "test.bam"),
+    (["-w", "1", "-q", "30", "-b", "25", "REGION"], "test.bam"),
+])
+def test_cli_warning_lines_match_the_reference_binary(tmp_path, args, bam):
+    """STDERR parity: the per-read warning lines (R:src/lib/bamrc/ReadWarnings.hpp:39-50) name the same reads, in the same order,
+    with the same "has been emitted N times" line, as the unmodified reference binary on the same command line."""
+    from oracle.oracle import REF_BIN, have_reference_binary
+    if not have_reference_binary():
+        pytest.skip("oracle/_ref not built")
+    exe = _cli()
+    ref = _write_ref(str(tmp_path))
+    out = {}
+    for name, binary in (("ours", exe), ("ref", REF_BIN)):
+        argv = [binary, "-f", ref]
+        regions = []
+        for a in args:
+            if a == "REGION":
+                regions = ["21:10402980-10402995"]
+            elif a == "site_list":
+                argv.append(os.path.join(GOLDEN, "site_list"))
+            else:
+                argv.append(a)
+        argv.append(os.path.join(GOLDEN, bam))
+        p = subprocess.run(argv + regions, capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()[-1000:]
+        out[name] = (p.stdout, p.stderr.decode("latin-1"))
+    assert out["ours"][0] == out["ref"][0]
+    assert out["ours"][1] == out["ref"][1]
+
+
+@pytest.mark.gpu
+def test_cli_region_forms_match_the_reference_binary(tmp_path):
+    """bam_parse_region corner cases: an open end keeps the previous / default beg-end, thousands separators are
+    accepted, "chr:-N" starts at the first base — STDOUT identical to the reference binary."""
+    from oracle.oracle import REF_BIN, have_reference_binary
+    if not have_reference_binary():
+        pytest.skip("oracle/_ref not built")
+    exe = _cli()
+    ref = _write_ref(str(tmp_path))
+    bam = os.path.join(GOLDEN, "test.bam")
+    for regions in (["21:10405200"], ["21:10402985-10402985", "21:10405200"], ["21:10,402,985-10,402,990"], ["21:10402985-"],
+                    ["21:10402985-10402985", "21"], ["21:-5"], ["21:10402985-10402986", "21:10402987-10402990"]):
+        o = subprocess.run([exe, "-w", "0", "-f", ref, bam] + regions, capture_output=True)
+        r = subprocess.run([REF_BIN, "-w", "0", "-f", ref, bam] + regions, capture_output=True)
+        assert o.returncode == r.returncode == 0
+        assert o.stdout == r.stdout, regions
+
+
+def test_cli_reports_truncated_bam(tmp_path):
+    """A BAM cut in the middle of a BGZF block is a decode ERROR, not end of file: non-zero exit and a diagnostic."""
+    exe = _cli()
+    src = open(os.path.join(GOLDEN, "test.bam"), "rb").read()
+    cut = os.path.join(str(tmp_path), "cut.bam")
+    open(cut, "wb").write(src[:60000])
+    import shutil
+    shutil.copy(os.path.join(GOLDEN, "test.bam.bai"), cut + ".bai")
+    env = dict(os.environ, BRC_CLI_DECODE_ONLY="1")
+    p = subprocess.run([exe, "-w", "0", cut, "21:10402000-10406000"], capture_output=True, env=env)
+    assert p.returncode == 1 and b"truncated or corrupt" in p.stderr
+    q = subprocess.run([exe, "-w", "0", os.path.join(GOLDEN, "test.bam"), "21:10402000-10406000"], capture_output=True, env=env)
+    assert q.returncode == 0 and b"truncated" not in q.stderr
+
+
+def _cram_fixture():
+    d = os.path.join(ROOT, "oracle", "_ref", "test-data")
+    if not os.path.exists(os.path.join(d, "twolib.sorted.cram")):
+        pytest.skip("oracle/_ref/test-data not present")
+    exe = _cli()
+    if b"BRC_WITH_HTSLIB" not in open(exe, "rb").read() and not os.path.exists(os.path.join(ROOT, "bam_readcount_b200", "third_party", "htslib", "libhts.a")):
+        pytest.skip("host built without htslib (tools/build_htslib.sh)")
+    return exe, d
+
+
+def test_cli_decodes_cram_through_htslib():
+    """BASELINE config 2b input: twolib.sorted.cram is decoded by the host (htslib), no device needed for the decode itself."""
+    exe, d = _cram_fixture()
+    p = subprocess.run([exe, "-w", "0", "-f", "rand1k.fa", "-l", "twolib_site_list.txt", "twolib.sorted.cram"], cwd=d, capture_output=True,
+                       env=dict(os.environ, BRC_CLI_DECODE_ONLY="1"))
+    assert p.returncode == 0, p.stderr.decode()
+    assert b"Expect library: reads1_lb in BAM" in p.stderr
+    tid, beg, end, n, psum, qsum = p.stdout.decode().split()
+    assert (tid, beg, end) == ("0", "49", "60") and int(n) >= 1 and int(qsum) == 255 * 60 * int(n)     # CRAM without qualities: 0xFF
+
+
+@pytest.mark.gpu
+def test_cli_cram_config_2b_matches_reference_output():
+    """BASELINE config 2b on twolib.sorted.cram itself (R:test-data/cram_site_test.sh:1): -p and all-library output equal the
+    committed output of the reference binary."""
+    exe, d = _cram_fixture()
+    for extra, golden in ((["-p"], "ref_cram_twolib_perlib.txt"), ([], "ref_cram_twolib_alllib.txt")):
+        p = subprocess.run([exe, "-w", "0"] + extra + ["-f", "rand1k.fa", "-l", "twolib_site_list.txt", "twolib.sorted.cram"], cwd=d, capture_output=True)
+        assert p.returncode == 0, p.stderr.decode()[-2000:]
+        assert p.stdout.decode("latin-1") == cases.load_golden_text(golden)

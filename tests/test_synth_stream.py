@@ -255,7 +255,8 @@ def test_windowed_device_path_equals_whole_region():
             want = whole.dump_range(hb, {1: (0, ref)}, 0, a, b)
             assert got == want
             s0 = w.beg - w.first_pos
-            assert int((r.ncover[0, s0:] > 0).sum()) == w.n_sites          # every site of the window is a position
+            uncovered = w.n_sites - int((r.ncover[0, s0:] > 0).sum())          # only the first bases of a contig can lack a spanning read
+            assert uncovered == 0 or (w.beg == 0 and uncovered < 64)
     finally:
         run.close()
     assert len(wdump) > 0
