@@ -529,7 +529,10 @@ void usage() {
                 "  -p [ --per-library ]                  report results by library.\n"
                 "  -w [ --max-warnings ] arg             maximum number of warnings of each type to emit. -1 gives an unlimited number.\n"
                 "  -i [ --insertion-centric ]            generate indel centric readcounts. Reads containing insertions will not be\n"
-                "                                        included in per-base counts\n\n");
+                "                                        included in per-base counts\n"
+                "  --shard RANK/COUNT                    (this host) compute only shard RANK of COUNT: the regions are cut into COUNT runs of\n"
+                "                                        about equal BAI-estimated coverage, one process per GPU (BRC_DEVICE); outputs\n"
+                "                                        concatenate in rank order\n\n");
 }
 
 // samtools region string "name[:beg[-end]]" as bam_parse_region (V:bam_aux.c:65-75) handles it.  Returns 0 when beg and end were
@@ -567,7 +570,8 @@ int main(int argc, char **argv) {
     std::string fn_pos, fn_fa, dist_arg;
     static option lo[] = {{"help", 0, 0, 'h'}, {"version", 0, 0, 'v'}, {"min-mapping-quality", 1, 0, 'q'}, {"min-base-quality", 1, 0, 'b'},
                           {"max-count", 1, 0, 'd'}, {"site-list", 1, 0, 'l'}, {"reference-fasta", 1, 0, 'f'}, {"print-individual-mapq", 1, 0, 'D'},
-                          {"per-library", 0, 0, 'p'}, {"max-warnings", 1, 0, 'w'}, {"insertion-centric", 0, 0, 'i'}, {0, 0, 0, 0}};
+                          {"per-library", 0, 0, 'p'}, {"max-warnings", 1, 0, 'w'}, {"insertion-centric", 0, 0, 'i'}, {"shard", 1, 0, 1000}, {0, 0, 0, 0}};
+    int shard_rank = 0, shard_count = 1;
     bool help = false, version = false;
     for (int c; (c = getopt_long(argc, argv, "hvq:b:d:l:f:D:pw:i", lo, nullptr)) != -1;) {
         switch (c) {
@@ -575,6 +579,7 @@ int main(int argc, char **argv) {
         case 'q': min_mapq = std::atoi(optarg); break; case 'b': min_bq = std::atoi(optarg); break; case 'd': max_cnt = std::atoi(optarg); break;
         case 'l': fn_pos = optarg; break; case 'f': fn_fa = optarg; break; case 'D': dist_arg = optarg; break;
         case 'p': per_lib = true; break; case 'w': max_warn = std::atoll(optarg); break; case 'i': ic = true; break;
+        case 1000: if (std::sscanf(optarg, "%d/%d", &shard_rank, &shard_count) != 2 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) { std::fprintf(stderr, "--shard wants RANK/COUNT with 0 <= RANK < COUNT\n"); return 1; } break;
         default: usage(); return 1;
         }
     }
@@ -671,7 +676,8 @@ int main(int argc, char **argv) {
     // (the 1-site halo), so the concatenated output equals the unsplit region's.  Only the last window of an argv region keeps
     // argv semantics.  (With a tiny -d the max-count rule sees the window's own fetch order)
     {
-        const int64_t W = std::getenv("BRC_CLI_WINDOW") ? std::atoll(std::getenv("BRC_CLI_WINDOW")) : 8000000;
+        int64_t W = std::getenv("BRC_CLI_WINDOW") ? std::atoll(std::getenv("BRC_CLI_WINDOW")) : 8000000;
+        if (shard_count > 1 && !std::getenv("BRC_CLI_WINDOW")) W = 1000000;      // finer units so the shards can balance
         std::vector<Region> cut;
         for (const Region &g : regions) {
             const int64_t clen = bam.lens[(size_t)g.tid];
@@ -685,6 +691,34 @@ int main(int argc, char **argv) {
             }
         }
         regions.swap(cut);
+    }
+
+    // --shard RANK/COUNT: one process per GPU.  The (windowed) regions are the units; each unit's weight is the
+    // compressed-byte span the BAI linear index gives for it — the coverage estimate the index offers without touching the data
+    // — and the units are cut into COUNT contiguous runs of about equal weight; this process computes run RANK.  Units are
+    // independent (every window recomputes its left halo site), so the concatenation of the ranks' outputs in rank order is the
+    // unsharded output; only the reference's never-cleared argv deletion queue does not cross a shard boundary.
+    if (shard_count > 1) {
+        std::vector<double> wgt(regions.size(), 1.0);
+        for (size_t i = 0; i < regions.size(); ++i) {
+            const Region &g = regions[i];
+            const int64_t clen = bam.lens[(size_t)g.tid];
+            const int64_t e_eff = std::min<int64_t>(g.end, std::max<int64_t>(clen, (int64_t)g.beg + 1));
+            double w = (double)std::max<int64_t>(e_eff - g.beg, 1) * 0.05;                 // no index information: 0.05 bytes per base
+            if (g.tid < (int)bam.idx.size() && !bam.idx[(size_t)g.tid].linear.empty()) {
+                const auto &lin = bam.idx[(size_t)g.tid].linear;
+                auto off_at = [&](int64_t p) { int64_t k = std::min<int64_t>(std::max<int64_t>(p >> 14, 0), (int64_t)lin.size() - 1); while (k > 0 && lin[(size_t)k] == 0) --k; return (double)(lin[(size_t)k] >> 16); };
+                const double d = off_at(e_eff + 16384) - off_at(g.beg);
+                if (d > 0) w = d * (double)(e_eff - g.beg) / (double)((((e_eff + 16384) >> 14) - (g.beg >> 14)) * 16384);
+            }
+            wgt[i] = w;
+        }
+        double tot = 0; for (double w : wgt) tot += w;
+        std::vector<size_t> cutpt((size_t)shard_count + 1, regions.size()); cutpt[0] = 0;
+        { double acc = 0; int r = 1; for (size_t i = 0; i < regions.size() && r < shard_count; ++i) { acc += wgt[i]; while (r < shard_count && acc >= tot * r / shard_count) cutpt[(size_t)r++] = i + 1; } }
+        std::vector<Region> mine(regions.begin() + (long)cutpt[(size_t)shard_rank], regions.begin() + (long)cutpt[(size_t)shard_rank + 1]);
+        if (std::getenv("BRC_CLI_TIMING")) std::fprintf(stderr, "[brc shard] %d/%d: units %zu..%zu of %zu\n", shard_rank, shard_count, cutpt[(size_t)shard_rank], cutpt[(size_t)shard_rank + 1], regions.size());
+        regions.swap(mine);
     }
 
     std::set<int> ref_loaded;

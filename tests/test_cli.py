@@ -412,3 +412,43 @@ def test_cli_cram_config_2b_matches_reference_output():
         p = subprocess.run([exe, "-w", "0"] + extra + ["-f", "rand1k.fa", "-l", "twolib_site_list.txt", "twolib.sorted.cram"], cwd=d, capture_output=True)
         assert p.returncode == 0, p.stderr.decode()[-2000:]
         assert p.stdout.decode("latin-1") == cases.load_golden_text(golden)
+
+
+def test_cli_shards_partition_the_regions(tmp_path):
+    """--shard RANK/COUNT: the ranks' units are a partition of the windowed regions, in order (decode-only, no device)."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import synth_cb
+    exe = _cli()
+    sp = synth_cb.Spec(seed=3, contig_len=1280 * 400)
+    info = synth_cb.write_sample_bam(sp, 0, 0, 400, str(tmp_path), REF_SAMTOOLS)
+    env = dict(os.environ, BRC_CLI_DECODE_ONLY="1", BRC_CLI_WINDOW="20000")
+    whole = subprocess.run([exe, "-w", "0", info["bam"], "chr1:1001-400000", "chr1:420001-500000"], capture_output=True, env=env)
+    assert whole.returncode == 0
+    parts = []
+    for r in range(3):
+        p = subprocess.run([exe, "-w", "0", "--shard", f"{r}/3", info["bam"], "chr1:1001-400000", "chr1:420001-500000"], capture_output=True, env=env)
+        assert p.returncode == 0, p.stderr.decode()
+        parts.append(p.stdout)
+    assert b"".join(parts) == whole.stdout and all(len(x) > 0 for x in parts)
+    sizes = [sum(int(l.split()[3]) for l in x.decode().splitlines()) for x in parts]      # records fetched per shard
+    assert max(sizes) < 1.35 * min(sizes)                                                   # BAI-weighted: about equal coverage
+
+
+@pytest.mark.gpu
+def test_cli_sharded_output_concatenates_to_the_unsharded_output(tmp_path):
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import synth_cb
+    exe = _cli()
+    sp = synth_cb.Spec(seed=8, contig_len=1280 * 300)
+    info = synth_cb.write_sample_bam(sp, 0, 0, 300, str(tmp_path), REF_SAMTOOLS)
+    env = dict(os.environ, BRC_CLI_WINDOW="50000")
+    args = ["-w", "0", "-i", "-f", info["fasta"], info["bam"], "chr1:2001-380000"]
+    whole = subprocess.run([exe] + args, capture_output=True, env=env)
+    assert whole.returncode == 0, whole.stderr.decode()[-1000:]
+    multi = subprocess.run(["bash", os.path.join(ROOT, "tools", "brc_multi.sh"), "3"] + args, capture_output=True, env=dict(env, BRC_NDEV="1"))
+    assert multi.returncode == 0, multi.stderr.decode()[-1000:]
+    assert multi.stdout == whole.stdout and len(whole.stdout.splitlines()) == 378000
