@@ -170,12 +170,15 @@ struct PileupParams {
 
 constexpr int DEEP_MAX_SITES = 2;
 constexpr int DEEP_THREADS = 256;
-// one owner thread per (site, library row, statistic): the tile qualifies only if they fit one CTA
+// one owner thread per (site, library row, statistic) must fit one CTA: a CTA takes the tile's sites x up to DEEP_ROWS library
+// rows; a -p tile with more libraries is spread over ceil(n_rows / DEEP_ROWS) CTAs (grid.y), each streaming the tile's reads and
+// keeping the events of its own rows
 // (integer, float and double statistics start on warp boundaries so a warp runs one kind of loop: 9G | 3G | G threads)
+constexpr int DEEP_ROWS = 8;
 __host__ __device__ inline int deep_flt_base(int G) { return (9 * G + 31) & ~31; }
 __host__ __device__ inline int deep_dbl_base(int G) { return (deep_flt_base(G) + 3 * G + 31) & ~31; }
 __host__ __device__ inline bool deep_shape_ok(int n_sites, int n_rows) {
-    const int G = n_sites * n_rows;
+    const int G = n_sites * (n_rows < DEEP_ROWS ? n_rows : DEEP_ROWS);
     return n_sites <= DEEP_MAX_SITES && G >= 1 && deep_dbl_base(G) + G <= DEEP_THREADS;
 }
 

@@ -1138,8 +1138,10 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
     const TileInfo ti = P.tiles[tile];
     int32_t lo = P.tile_lo[tile], hi = P.tile_hi[tile];
     if (lo >= hi) { lo = 0; hi = 0; }
-    const int n_rows = P.res.n_rows;
-    if (!deep_shape_ok(ti.n, n_rows) || hi - lo < P.deep_min_reads) return;   // pileup_kernel computes it (same predicate)
+    // this CTA's library rows [row0, row0 + n_rows): n_rows <= DEEP_ROWS, all of them in all-library mode (one row)
+    const int row0 = (int)blockIdx.y * DEEP_ROWS;
+    const int n_rows = min(DEEP_ROWS, P.res.n_rows - row0);
+    if (!deep_shape_ok(ti.n, P.res.n_rows) || hi - lo < P.deep_min_reads) return;   // pileup_kernel computes it (same predicate)
     const int G = ti.n * n_rows;
 
     deep_fetch(P, sm.stage[0], lo + tid, hi, tid);
@@ -1158,7 +1160,7 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
     }
     uint32_t acc_u = 0u; float acc_f = 0.0f; double acc_d = 0.0;
     uint32_t pbase = NO_BASE; int32_t sec_head = -1;
-    const uint32_t oslot = owner ? (uint32_t)((int64_t)(og % n_rows) * P.res.n_slots + ti.slot0 + og / n_rows) : 0u;   // row * n_slots + slot of the owner's group
+    const uint32_t oslot = owner ? (uint32_t)((int64_t)(row0 + og % n_rows) * P.res.n_slots + ti.slot0 + og / n_rows) : 0u;   // row * n_slots + slot of the owner's group
     uint32_t warn_nm = 0u, warn_sm = 0u;
 #ifdef BRC_DEEP_PROFILE
     long long prof[6] = {0, 0, 0, 0, 0, 0};
@@ -1200,9 +1202,9 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_site_kernel(PileupParams
             if (!cover[sg]) continue;
             uint32_t row = 0u;
             if (PER_LIB) {
-                if (lib == LIB_NONE || lib >= (uint32_t)n_rows) continue;
+                if (lib == LIB_NONE || lib < (uint32_t)row0 || lib >= (uint32_t)(row0 + n_rows)) continue;   // another CTA's library
                 if (r > sm.first_libless[sg]) continue;          // pileup_func returned early at this site (R:...:281-284)
-                row = lib;
+                row = lib - (uint32_t)row0;
             }
             grp[sg] = sg * n_rows + (int)row;
             gcov[sg] = grp[sg];                                  // counts as a covering read of (site, row)
@@ -1420,8 +1422,9 @@ cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s) {
         if (e2 != cudaSuccess) return e2;
         attr_set[dev] = true;
     }
-    if (p.per_lib) deep_site_kernel<true><<<(unsigned)p.n_deep, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);
-    else deep_site_kernel<false><<<(unsigned)p.n_deep, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);
+    const dim3 grid((unsigned)p.n_deep, (unsigned)((p.res.n_rows + DEEP_ROWS - 1) / DEEP_ROWS));   // y: batches of DEEP_ROWS libraries
+    if (p.per_lib) deep_site_kernel<true><<<grid, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);
+    else deep_site_kernel<false><<<grid, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);
     return cudaGetLastError();
 }
 

@@ -71,6 +71,21 @@ def test_deep_site_kernel_is_what_runs_on_a_deep_panel(monkeypatch):
     assert d1 == od
 
 
+@pytest.mark.parametrize("n_libs", [12, 19])
+def test_deep_site_kernel_with_more_than_eight_libraries(n_libs, monkeypatch):
+    """-p panels with more libraries than one CTA's owner threads hold: the tile's libraries are spread over several CTAs
+    (grid.y batches of 8), each streaming the tile's reads; identical to the oracle and to pileup_kernel."""
+    case = cases.deep_case(n_sites=2, depth=3000, seed=13, n_libs=n_libs)
+    fl = dict(per_lib=True, max_cnt=100000000, min_bq=10)
+    _, d1, w1, _ = cases.run_engine(case, fl, site_list=True, want_dump=True)
+    _, od, ow = cases.run_oracle(case, fl, site_list=True)
+    assert d1 == od, _first_diff(d1, od)
+    assert (w1[0], w1[1], w1[3]) == ow
+    monkeypatch.setenv("BRC_DEEP_MIN_READS", "2147483647")
+    _, d2, _, _ = cases.run_engine(case, fl, site_list=True, want_dump=True)
+    assert d2 == od
+
+
 def test_exact_arithmetic_shortcuts_match_ieee_intrinsics():
     """K1 replaces __fdiv_rn by a reciprocal + one FMA correction and float<->double conversions by bit
     casts for read lengths <= 2048; every (numerator, divisor) pair it can see must agree with IEEE."""
