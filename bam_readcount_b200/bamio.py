@@ -159,3 +159,104 @@ class Fasta:
             fh.seek(fo)
             raw = fh.read(fe - fo)
         return raw.replace(b"\n", b"").replace(b"\r", b"")
+
+
+# ------------------------------------------------------------------------------------------------
+# BAI (SAM spec §5.2) and BGZF spans for the device decoder (engine: brc_push_bam_span)
+# ------------------------------------------------------------------------------------------------
+class BaiIndex:
+    """Bins, chunks and the 16 kb linear index of every reference: the virtual offsets in it are starts of real records."""
+
+    def __init__(self, path: str):
+        d = open(path, "rb").read()
+        assert d[:4] == b"BAI\1", "not a BAI file"
+        o = 4
+        n_ref, = struct.unpack_from("<i", d, o); o += 4
+        self.bins: List[Dict[int, List[Tuple[int, int]]]] = []
+        self.linear: List[np.ndarray] = []
+        for _ in range(n_ref):
+            n_bin, = struct.unpack_from("<i", d, o); o += 4
+            bins: Dict[int, List[Tuple[int, int]]] = {}
+            for _ in range(n_bin):
+                b, n_chunk = struct.unpack_from("<Ii", d, o); o += 8
+                ch = [struct.unpack_from("<QQ", d, o + 16 * k) for k in range(n_chunk)]
+                o += 16 * n_chunk
+                if b != 37450:
+                    bins[b] = ch
+            n_intv, = struct.unpack_from("<i", d, o); o += 4
+            self.linear.append(np.frombuffer(d, dtype="<u8", count=n_intv, offset=o).copy())
+            o += 8 * n_intv
+            self.bins.append(bins)
+
+    @staticmethod
+    def reg2bins(beg: int, end: int) -> List[int]:
+        end -= 1
+        out = [0]
+        for shift, off in ((26, 1), (23, 9), (20, 73), (17, 585), (14, 4681)):
+            out += list(range(off + (beg >> shift), off + (end >> shift) + 1))
+        return out
+
+    def window_weights(self, tid: int, n_windows: int) -> np.ndarray:
+        """Compressed bytes per 16 kb window from the linear index: the coverage proxy shards are balanced by."""
+        lin = self.linear[tid].astype(np.int64) >> 16
+        w = np.zeros(n_windows, dtype=np.float64)
+        if lin.size < 2:
+            return w
+        filled = lin.copy()
+        for i in range(1, filled.size):
+            if filled[i] == 0:
+                filled[i] = filled[i - 1]
+        d = np.diff(filled).clip(min=0)
+        w[:min(n_windows, d.size)] = d[:n_windows]
+        return w
+
+
+def bam_span(bam_path: str, bai: BaiIndex, tid: int, beg: int, end: int, rg_lib: Optional[Dict[str, int]] = None) -> Optional[dict]:
+    """The compressed bytes and index entry points that cover every record overlapping [beg, end) of `tid` — what
+    samfetch(tid, beg, end) would read — for brc_push_bam_span.  None when the index has nothing there."""
+    chunks = []
+    min_lin = int(bai.linear[tid][min(beg >> 14, bai.linear[tid].size - 1)]) if bai.linear[tid].size else 0
+    for b in BaiIndex.reg2bins(max(beg, 0), max(end, beg + 1)):
+        for cb, ce in bai.bins[tid].get(b, ()):
+            if ce > min_lin:
+                chunks.append((max(cb, min_lin), ce))
+    if not chunks:
+        return None
+    v0 = min(c[0] for c in chunks)
+    v1 = max(c[1] for c in chunks)
+    c0, c1 = v0 >> 16, v1 >> 16
+    with open(bam_path, "rb") as fh:
+        fh.seek(c0)
+        head = fh.read(c1 - c0 + 65536 + 32)
+    # whole blocks from c0 through the block that holds v1
+    o, blocks = 0, []
+    while o + 18 <= len(head):
+        xlen = head[o + 10] | (head[o + 11] << 8)
+        bsize, i = -1, 0
+        while i + 4 <= xlen:
+            sl = head[o + 12 + i + 2] | (head[o + 12 + i + 3] << 8)
+            if head[o + 12 + i:o + 12 + i + 2] == b"BC":
+                bsize = head[o + 12 + i + 4] | (head[o + 12 + i + 5] << 8)
+            i += 4 + sl
+        if bsize < 0 or o + bsize + 1 > len(head):
+            break
+        blocks.append(o)
+        o += bsize + 1
+        if c0 + blocks[-1] >= c1:
+            break
+    comp = head[:o]
+    in_span = {c0 + b for b in blocks}
+    # entry points: v0, the chunk starts and the linear-index offsets that fall inside the span
+    cand = {v0}
+    for cb, _ in chunks:
+        cand.add(cb)
+    lin = bai.linear[tid]
+    for w in range(min(beg >> 14, lin.size), min((end >> 14) + 2, lin.size)):
+        cand.add(int(lin[w]))
+    for b in BaiIndex.reg2bins(max(beg, 0), max(end, beg + 1)):
+        for cb, _ in bai.bins[tid].get(b, ()):
+            cand.add(cb)
+    entries = sorted(v for v in cand if v0 <= v < v1 and (v >> 16) in in_span)
+    rel = lambda v: (((v >> 16) - c0) << 16) | (v & 0xFFFF)      # noqa: E731
+    return dict(comp=comp, entries=[rel(v) for v in entries], end_voff=rel(v1) if (v1 >> 16) in in_span else -1, tid=tid,
+                rg_lib=dict(rg_lib or {}))

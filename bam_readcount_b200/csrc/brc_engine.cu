@@ -81,6 +81,8 @@ void brc_destroy(brc_engine *e) {
                       &e->d_words, &e->d_sec, &e->d_sec_count, &e->d_warn};
     for (auto *b : bufs) b->release();
     for (auto &b : e->d_in) b.release();
+    { brc_engine::Decoded &D = e->dec; DevBuf *db[] = {&D.comp, &D.btab, &D.u, &D.meta, &D.scratch, &D.count, &D.partial, &D.cigar, &D.seq, &D.qual, &D.ins_idx, &D.ins_out};
+      for (auto *b : db) b->release(); for (auto &b : D.arr) b.release(); }
     PinBuf *pins[] = {&e->h_words, &e->h_sec, &e->h_misc};
     for (auto *b : pins) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -148,6 +150,7 @@ int brc_reset(brc_engine *e) {
     if (e->h2d_chunks) { cudaSetDevice(e->cfg.device); cudaStreamSynchronize(e->s_in); e->h2d_chunks = 0; }
     e->reads.clear(); e->is_borrowed = false; e->regions.clear(); e->region_open = false; e->adm.reset(); e->n_indel_ops = 0;
     e->results_valid = false; e->planned = false; e->tiles.clear(); e->regions_dev.clear(); e->n_slots = 0; e->wide.valid = false;
+    e->dec.pushed = false; e->dec.ins_reads.clear(); e->dec.ins_off.clear(); e->dec.ins_pool.clear();
     for (auto &w : e->warn_counts) w = 0;
     return BRC_OK;
 }
@@ -328,6 +331,23 @@ int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
                                b->qual + b->qual_off[i]);
         if (rc != BRC_OK) return rc;
     }
+    return BRC_OK;
+}
+
+// f-2 region-loop form: the compressed span IS the region's read stream; decoded on the device right away (the count and the
+// largest bam_endpos come back with one synchronisation), computed by brc_compute without the reads ever being on the host.
+int brc_push_bam_span(brc_engine *e, const brc_bam_span *span) {
+    if (!e || !span) return BRC_E_INVALID;
+    if (!e->region_open) return set_error(e, BRC_E_INVALID, "push_bam_span: no open region");
+    if (e->regions.size() != 1 || e->n_host_reads() != 0 || e->dec.pushed) return set_error(e, BRC_E_INVALID, "push_bam_span: must be the only data pushed since brc_reset (one region, one span)");
+    brc_read_batch dev{};
+    int rc = brc_decode_bam_span(e, span, &dev, e->stream);
+    if (rc != BRC_OK) return rc;
+    if (dev.n_reads >= (int64_t)e->cfg.max_cnt) return set_error(e, BRC_E_INVALID, "push_bam_span: -d is smaller than the region's read count; use brc_push_read (host admission)");
+    brc_region &rg = e->regions.back();
+    rg.read_lo = 0; rg.read_hi = dev.n_reads;
+    if (e->dec.max_end > e->open_max_end) e->open_max_end = e->dec.max_end;
+    e->dec.pushed = true;
     return BRC_OK;
 }
 
@@ -651,6 +671,32 @@ int brc_compute(brc_engine *e) {
     cudaSetDevice(e->cfg.device);
     int rc = build_geometry(e, e->regions.data(), (int64_t)e->regions.size());
     if (rc != BRC_OK) return rc;
+    if (e->dec.pushed) {
+        // f-2: the region's reads were inflated and framed on the device (brc_push_bam_span): kernels straight on that batch
+        if (!e->dec.valid || e->regions.size() != 1) return set_error(e, BRC_E_INVALID, "compute: the device-decoded batch is gone");
+        if (!find_ref(e, e->regions[0].tid)) return set_error(e, BRC_E_NO_REFERENCE, "no reference for contig");
+        const brc_read_batch &b = e->dec.batch;
+        rc = alloc_outputs(e, b.n_reads);
+        if (rc != BRC_OK) return rc;
+        cudaStream_t sd = e->stream;
+        ReadsDev &R = e->dev_reads;
+        R.n_reads = b.n_reads; R.pos = b.pos; R.flag = b.flag; R.mapq = b.mapq; R.lib = b.lib; R.l_qseq = b.l_qseq; R.nm = b.nm; R.sm = b.sm;
+        R.cigar_off = b.cigar_off; R.cigar = b.cigar; R.seq_off = b.seq_off; R.seq = b.seq; R.qual_off = b.qual_off; R.qual = b.qual;
+        rc = upload_geometry(e, sd);
+        if (rc != BRC_OK) return rc;
+        int64_t capd = std::max<int64_t>(e->sec_cap, (int64_t)e->n_rows * e->n_slots / 6 + b.n_reads / 8 + 1024);
+        for (int attempt = 0; attempt < 8; ++attempt) {
+            rc = alloc_sec(e, capd);
+            if (rc != BRC_OK) return rc;
+            rc = run_kernels(e, nullptr, sd, true);
+            if (rc != BRC_E_OVERFLOW) break;
+            capd = std::max<int64_t>(capd * 2, e->h_n_sec + 1024);
+        }
+        if (rc != BRC_OK) return rc == BRC_E_OVERFLOW ? set_error(e, rc, "secondary key pool overflow") : rc;
+        rc = fetch_results(e, sd);
+        if (rc != BRC_OK) return rc;
+        return brc::fetch_insertion_reads(e, sd);
+    }
     HostReads &H = e->reads;
     const bool bw = e->is_borrowed;
     const brc_read_batch &B = e->borrowed;

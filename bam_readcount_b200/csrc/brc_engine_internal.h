@@ -146,6 +146,29 @@ struct brc_engine {
     // text of the last brc_format_* call, so the usual size-query + fill pair formats only once
     std::vector<std::string> fmt_parts; int64_t fmt_key[3] = {-2, -2, -2}; bool fmt_valid = false;
 
+    // f-2: a batch inflated + framed on the device from BGZF blocks (brc_bgzf.cu)
+    struct Decoded {
+        brc::DevBuf comp, btab, u, meta, scratch, count, partial, arr[12], cigar, seq, qual, ins_idx, ins_out;
+        brc_read_batch batch{};          // device pointers into the buffers above
+        int64_t n_reads = 0, max_end = 0, n_cigar = 0, n_seq = 0, n_qual = 0, h2d_bytes = 0;
+        int kernels = 0;
+        bool valid = false;              // a decoded batch is resident
+        bool pushed = false;             // ... and it is the open / only region's read stream (brc_push_bam_span)
+        std::vector<std::vector<uint8_t>> host;   // brc_fetch_decoded_batch
+        // packed bases of the reads that carry an insertion allele (the text emitter prints them), fetched after the kernels
+        std::vector<int64_t> ins_reads; std::vector<uint64_t> ins_off; std::vector<uint8_t> ins_pool;
+    } dec;
+    // packed bases of read `r` of the pushed stream, wherever they live on the host (staging copy, borrowed batch, or the
+    // sparse copy of a device-decoded batch); nullptr when unknown
+    const uint8_t *host_read_seq(int64_t r) const {
+        if (dec.pushed) {
+            const auto it = std::lower_bound(dec.ins_reads.begin(), dec.ins_reads.end(), r);
+            if (it == dec.ins_reads.end() || *it != r) return nullptr;
+            return dec.ins_pool.data() + dec.ins_off[(size_t)(it - dec.ins_reads.begin())];
+        }
+        return host_seq() + host_seq_off()[(size_t)r];
+    }
+
     // deletion queue carried from one formatting pass to the next (brc_set_queue_carry): lets a caller flush argv regions
     // batch by batch and still reproduce the reference's never-cleared queue
     bool carry_on = false;
@@ -158,5 +181,6 @@ namespace brc {
 int set_error(brc_engine *e, int status, const std::string &msg);
 int set_cuda_error(brc_engine *e, cudaError_t ce, const char *what);
 const HostRef *find_ref(const brc_engine *e, int32_t tid);
+int fetch_insertion_reads(brc_engine *e, cudaStream_t s);   // brc_bgzf.cu
 void ensure_wide(brc_engine *e);   // expand the packed host records into e->wide (multi-threaded; no-op when already done)
 }  // namespace brc

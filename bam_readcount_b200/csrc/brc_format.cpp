@@ -106,8 +106,8 @@ void format_site(const View &V, int32_t s, const char *const *lib_names, EmitSta
             Indel in; in.st = t;
             if (V.skind[j] == BRC_KIND_INS) {          // "+" + canonicalised read bases qpos+1..qpos+len  (R:...:324-330)
                 in.allele = "+";
-                const uint8_t *sq = V.h_seq + V.h_seq_off[(size_t)V.sread[j]];
-                for (int k = 1; k <= V.slen[j]; ++k) { int i = V.sqpos[j] + k; uint8_t b = sq[i >> 1]; in.allele += kNt[kCanon[(i & 1) ? (b & 15) : (b >> 4)]]; }
+                const uint8_t *sq = V.e->host_read_seq(V.sread[j]);
+                for (int k = 1; k <= V.slen[j]; ++k) { int i = V.sqpos[j] + k; uint8_t b = sq ? sq[i >> 1] : (uint8_t)0xFF; in.allele += kNt[kCanon[(i & 1) ? (b & 15) : (b >> 4)]]; }
             } else {                                   // "-" + raw reference characters pos+1..pos+len (R:...:331-339)
                 in.allele = "-";
                 for (int k = 1; k <= V.slen[j]; ++k) {
@@ -286,7 +286,7 @@ extern "C" int brc_set_queue_carry(brc_engine *e, int on) {
 extern "C" int64_t brc_format_text(brc_engine *e, int64_t region_index, const char *const *lib_names, char *buf, int64_t cap) {
     if (!e) return BRC_E_INVALID;
     if (!e->results_valid) return brc::set_error(e, BRC_E_INVALID, "format_text: no results");
-    if (e->n_host_reads() == 0 && e->h_n_sec > 0) return brc::set_error(e, BRC_E_INVALID, "format_text: needs the pushed reads (push path only)");
+    if (e->n_host_reads() == 0 && e->h_n_sec > 0 && !e->dec.pushed) return brc::set_error(e, BRC_E_INVALID, "format_text: needs the pushed reads (push path only)");
     if (region_index >= (int64_t)e->regions.size()) return BRC_E_INVALID;
     return serve(e, region_index < 0 ? -1 : region_index, -1, -1, lib_names, buf, cap);
 }

@@ -59,6 +59,11 @@ class CResults(C.Structure):
                 ("sec_stats", C.c_void_p)]
 
 
+class CBamSpan(C.Structure):
+    _fields_ = [("comp", C.c_void_p), ("comp_len", C.c_int64), ("n_entry", C.c_int64), ("entry", C.c_void_p), ("end_voff", C.c_int64),
+                ("tid", C.c_int32), ("n_rg", C.c_int32), ("rg_id", C.c_void_p), ("rg_lib", C.c_void_p)]
+
+
 class CSecRecord(C.Structure):
     _fields_ = [("slot", C.c_uint32), ("next", C.c_int32), ("kind_len", C.c_uint32), ("read", C.c_int32), ("qpos", C.c_int32),
                 ("stats", C.c_uint32 * 13)]
@@ -75,7 +80,7 @@ SEC_RECORD_BYTES = 72
 
 EXPORTS = [
     "brc_abi_version", "brc_create", "brc_destroy", "brc_last_error", "brc_strerror", "brc_set_reference", "brc_set_reference_device", "brc_reset",
-    "brc_begin_region", "brc_push_read", "brc_push_reads", "brc_end_region", "brc_compute", "brc_get_results",
+    "brc_begin_region", "brc_push_read", "brc_push_reads", "brc_end_region", "brc_decode_bam_span", "brc_push_bam_span", "brc_fetch_decoded_batch", "brc_compute", "brc_get_results",
     "brc_get_warning_counts", "brc_format_text", "brc_format_window", "brc_write_text", "brc_set_queue_carry", "brc_plan_device", "brc_run_device", "brc_device_packed_results", "brc_get_packed_results",
     "brc_fetch_device_results", "brc_last_launch_count", "brc_last_stage_ms", "brc_selftest_fastmath",
 ]
@@ -108,6 +113,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                                   C.c_int32, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.brc_push_reads.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
     lib.brc_end_region.argtypes = [C.c_void_p]
+    lib.brc_decode_bam_span.argtypes = [C.c_void_p, C.POINTER(CBamSpan), C.POINTER(CReadBatch), C.c_void_p]
+    lib.brc_push_bam_span.argtypes = [C.c_void_p, C.POINTER(CBamSpan)]
+    lib.brc_fetch_decoded_batch.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
     lib.brc_compute.argtypes = [C.c_void_p]
     lib.brc_get_results.argtypes = [C.c_void_p, C.POINTER(CResults)]
     lib.brc_get_warning_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -363,6 +371,40 @@ class Engine:
         cb = self.c_batch(b, keep)
         self._keep.append(keep)
         self._check(self.lib.brc_push_reads(self.h, C.byref(cb)))
+
+    # ---- f-2: compressed BGZF span -> device-decoded reads -------------------------------------------------
+    def _c_span(self, span: dict):
+        comp = np.frombuffer(span["comp"], dtype=np.uint8)
+        ent = np.asarray(span["entries"], dtype=np.uint64)
+        rg = list(span.get("rg_lib", {}).items())
+        ids = (C.c_char_p * max(1, len(rg)))(*[k.encode() for k, _ in rg])
+        libs = np.asarray([v for _, v in rg] or [0], dtype=np.uint16)
+        cs = CBamSpan(comp.ctypes.data, comp.size, ent.size, ent.ctypes.data, int(span.get("end_voff", -1)), int(span["tid"]), len(rg),
+                      C.cast(ids, C.c_void_p), libs.ctypes.data)
+        return cs, (comp, ent, ids, libs)
+
+    def push_bam_span(self, span: dict):
+        """The open region's reads as a compressed BGZF span (bamio.bam_span): inflated and framed on the device."""
+        cs, keep = self._c_span(span)
+        self._keep.append(keep)
+        self._check(self.lib.brc_push_bam_span(self.h, C.byref(cs)))
+
+    def decode_bam_span(self, span: dict) -> ReadBatch:
+        """Decode only, and copy the batch back to the host (tests: device decoder == host decoder)."""
+        cs, keep = self._c_span(span)
+        dev = CReadBatch()
+        self._check(self.lib.brc_decode_bam_span(self.h, C.byref(cs), C.byref(dev), None))
+        hb = CReadBatch()
+        self._check(self.lib.brc_fetch_decoded_batch(self.h, C.byref(hb)))
+        n = int(hb.n_reads)
+        co = _np_view(hb.cigar_off, n + 1, np.uint64).copy()
+        so = _np_view(hb.seq_off, n + 1, np.uint64).copy()
+        qo = _np_view(hb.qual_off, n + 1, np.uint64).copy()
+        return ReadBatch(tid=np.full(n, int(span["tid"]), np.int32), pos=_np_view(hb.pos, n, np.int32).copy(), flag=_np_view(hb.flag, n, np.uint16).copy(),
+                         mapq=_np_view(hb.mapq, n, np.uint8).copy(), lib=_np_view(hb.lib, n, np.uint16).copy(), l_qseq=_np_view(hb.l_qseq, n, np.int32).copy(),
+                         nm=_np_view(hb.nm, n, np.int32).copy(), sm=_np_view(hb.sm, n, np.int32).copy(), cigar_off=co,
+                         cigar=_np_view(hb.cigar, int(co[n]) if n else 0, np.uint32).copy(), seq_off=so, seq=_np_view(hb.seq, int(so[n]) if n else 0, np.uint8).copy(),
+                         qual_off=qo, qual=_np_view(hb.qual, int(qo[n]) if n else 0, np.uint8).copy(), qname=None)
 
     def end_region(self):
         self._check(self.lib.brc_end_region(self.h))

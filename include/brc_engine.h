@@ -227,6 +227,32 @@ BRC_API int brc_push_read(brc_engine *e, int32_t tid, int32_t pos, uint16_t flag
 BRC_API int brc_push_reads(brc_engine *e, const brc_read_batch *batch);
 BRC_API int brc_end_region(brc_engine *e);
 
+/* ---- f-2: BAM records straight from the file's BGZF blocks, inflated and framed ON THE DEVICE -------------------------
+ * (V:htslib-1.10/bgzf.c:697,897 inflate_block / bgzf_read_block; V:htslib-1.10/sam.c:598-659 bam_read1.)  Only the COMPRESSED
+ * bytes cross PCIe.  `comp` holds consecutive whole BGZF blocks; `entry` lists record starts the index knows inside them
+ * (BAI linear-index / bin-chunk virtual offsets are starts of real records), each encoded as
+ * (byte offset of its block inside comp) << 16 | offset inside that block's inflated data, ascending, entry[0] = the first
+ * record wanted.  Every entry starts an independent chain of block_size hops, so framing needs no guessing.  Records whose
+ * refID differs from `tid` are kept but never admitted.  Read groups: rg_id[i] -> rg_lib[i] (library rank or BRC_LIB_NONE).
+ * The -d max-count rule is not evaluated on this path (use brc_push_read when -d is smaller than the region's read count). */
+typedef struct {
+    const uint8_t *comp;
+    int64_t comp_len;
+    int64_t n_entry;
+    const uint64_t *entry;
+    int64_t end_voff;             /* records starting at or after it are not decoded (same encoding); < 0: to the end of the span */
+    int32_t tid;
+    int32_t n_rg;
+    const char *const *rg_id;
+    const uint16_t *rg_lib;
+} brc_bam_span;
+/* decode only: the batch (DEVICE pointers, engine-owned until the next decode) a caller can hand to brc_run_device */
+BRC_API int brc_decode_bam_span(brc_engine *e, const brc_bam_span *span, brc_read_batch *dev_batch_out, void *stream);
+/* region loop form: the span is the open region's read stream (instead of brc_push_read(s)); brc_compute then runs on it */
+BRC_API int brc_push_bam_span(brc_engine *e, const brc_bam_span *span);
+/* test / debug: the decoded batch copied to engine-owned HOST memory */
+BRC_API int brc_fetch_decoded_batch(brc_engine *e, brc_read_batch *host_out);
+
 /* Runs the GPU path over everything pushed since brc_reset: H2D, per-read precompute kernel,
  * pileup/accumulate kernel, D2H.  Reads not admitted by the pileup buffer (tid<0, FUNMAP,
  * the -d rule of V:htslib-1.10/sam.c:4491) are dropped on the host while batching. */
