@@ -169,7 +169,7 @@ struct BamFile {
     std::map<std::string, int> tid_of;
     uint64_t first_rec = 0;
     // BAI
-    struct RefIdx { std::vector<uint64_t> linear; uint64_t min_chunk = ~0ull; };
+    struct RefIdx { std::vector<uint64_t> linear; uint64_t min_chunk = ~0ull; std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins; };
     std::vector<RefIdx> idx;
     bool have_idx = false;
 
@@ -208,7 +208,7 @@ struct BamFile {
                 uint32_t bin; int32_t n_chunk; ok = rd(&bin, 4) && rd(&n_chunk, 4);
                 for (int c = 0; ok && c < n_chunk; ++c) {
                     uint64_t cb, ce; ok = rd(&cb, 8) && rd(&ce, 8);
-                    if (ok && bin != 37450) idx[(size_t)r].min_chunk = std::min(idx[(size_t)r].min_chunk, cb);
+                    if (ok && bin != 37450) { idx[(size_t)r].min_chunk = std::min(idx[(size_t)r].min_chunk, cb); idx[(size_t)r].bins[bin].push_back({cb, ce}); }
                 }
             }
             int32_t n_intv; ok = ok && rd(&n_intv, 4);
@@ -292,6 +292,53 @@ int64_t rec_endpos(const Rec &r) {   // bam_endpos
     }
     return (int64_t)r.pos + 1;
 }
+
+// ------------------------------------------------------------------------------------------
+// the compressed bytes + index entry points covering samfetch(tid, fbeg, fend), for brc_push_bam_span — the
+// records are inflated and framed on the device, only compressed bytes cross PCIe.  The BAI's chunk begins and linear-index
+// offsets are starts of real records: each starts an independent framing chain.
+// ------------------------------------------------------------------------------------------
+struct SpanBuilder {
+    std::vector<uint8_t> comp; std::vector<uint64_t> entries; int64_t end_voff = -1;
+    bool build(BamFile &bam, int tid, int64_t fbeg, int64_t fend) {
+        if (tid < 0 || tid >= (int)bam.idx.size()) return false;
+        const BamFile::RefIdx &ri = bam.idx[(size_t)tid];
+        uint64_t min_lin = 0;
+        if (!ri.linear.empty()) { int64_t w = std::min<int64_t>(fbeg >> 14, (int64_t)ri.linear.size() - 1); min_lin = ri.linear[(size_t)w]; }
+        uint64_t v0 = ~0ull, v1 = 0; std::vector<uint64_t> cand;
+        const int64_t b = std::max<int64_t>(fbeg, 0), e = std::max<int64_t>(fend, b + 1) - 1;
+        auto visit = [&](uint32_t bin) {
+            auto it = ri.bins.find(bin);
+            if (it == ri.bins.end()) return;
+            for (const auto &c : it->second) if (c.second > min_lin) { const uint64_t cb = std::max(c.first, min_lin); v0 = std::min(v0, cb); v1 = std::max(v1, c.second); cand.push_back(cb); }
+        };
+        visit(0);
+        const int sh[5] = {26, 23, 20, 17, 14}; const uint32_t of[5] = {1, 9, 73, 585, 4681};
+        for (int l = 0; l < 5; ++l) for (int64_t k = b >> sh[l]; k <= (e >> sh[l]); ++k) visit(of[l] + (uint32_t)k);
+        if (v0 == ~0ull || v1 <= v0) return false;
+        for (int64_t w = std::min<int64_t>(b >> 14, (int64_t)ri.linear.size()); w < std::min<int64_t>((e >> 14) + 2, (int64_t)ri.linear.size()); ++w) cand.push_back(ri.linear[(size_t)w]);
+        const uint64_t c0 = v0 >> 16, c1 = v1 >> 16;
+        comp.resize((size_t)(c1 - c0) + 65536 + 32);
+        if (fseeko(bam.bz.fp, (off_t)c0, SEEK_SET) != 0) return false;
+        const size_t got = std::fread(comp.data(), 1, comp.size(), bam.bz.fp);
+        std::vector<uint64_t> starts; size_t o = 0;
+        while (o + 18 <= got) {
+            size_t hdr = 0; const size_t tot = Bgzf::block_size(comp.data() + o, got - o, hdr);
+            if (!tot || o + tot > got) break;
+            starts.push_back(c0 + o); o += tot;
+            if (starts.back() >= c1) break;
+        }
+        if (starts.empty()) return false;
+        comp.resize(o);
+        auto rel = [&](uint64_t v, uint64_t &out) { const uint64_t co = v >> 16; if (!std::binary_search(starts.begin(), starts.end(), co)) return false; out = ((co - c0) << 16) | (v & 0xFFFF); return true; };
+        std::sort(cand.begin(), cand.end()); cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        entries.clear();
+        for (uint64_t v : cand) { uint64_t r; if (v >= v0 && v < v1 && rel(v, r)) entries.push_back(r); }
+        uint64_t r1; end_voff = rel(v1, r1) ? (int64_t)r1 : -1;
+        bam.bz.block.clear(); bam.bz.ahead.clear(); bam.bz.ahead_pos = 0; bam.bz.eof = false;     // the reader's position is stale now
+        return !entries.empty();
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // samfetch(in, idx, tid, fbeg, fend) for a run of regions.  The reference re-seeks through the index and
@@ -726,6 +773,11 @@ int main(int argc, char **argv) {
     const bool timing = std::getenv("BRC_CLI_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_decode = 0, t_compute = 0, t_format = 0, t_write = 0, t_ref = 0;
+    // BRC_CLI_DEVICE_DECODE=1: BGZF inflate + BAM framing on the GPU (per-read warning lines need host-decoded reads: counts only)
+    const bool device_decode = std::getenv("BRC_CLI_DEVICE_DECODE") != nullptr && !decode_only;
+    std::vector<std::string> rg_id_store; std::vector<const char *> rg_ids; std::vector<uint16_t> rg_libs;
+    for (const auto &kv : rg_lb) rg_id_store.push_back(kv.first);
+    for (const auto &id : rg_id_store) { rg_ids.push_back(id.c_str()); rg_libs.push_back(lib_rank[rg_lb[id]]); }
     Warner warner(max_warn, min_mapq, min_bq, per_lib, ic);
     int64_t warn_total[4] = {0, 0, 0, 0};
     auto flush = [&]() -> int {
@@ -789,6 +841,22 @@ int main(int argc, char **argv) {
         // samfetch(in, idx, ref, d.beg-1, d.end): records with tid, endpos > max(beg-1,0), pos < end, in file order
         const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
         int push_rc = BRC_OK;
+        if (device_decode && !is_cram) {
+            // f-2: hand the engine the compressed span; it inflates, frames and computes on the device.  One span per batch.
+            SpanBuilder sb;
+            if (sb.build(bam, g.tid, fbeg, fend)) {
+                brc_bam_span sp{}; sp.comp = sb.comp.data(); sp.comp_len = (int64_t)sb.comp.size(); sp.n_entry = (int64_t)sb.entries.size(); sp.entry = sb.entries.data();
+                sp.end_voff = sb.end_voff; sp.tid = g.tid; sp.n_rg = (int32_t)rg_ids.size(); sp.rg_id = rg_ids.data(); sp.rg_lib = rg_libs.data();
+                const int prc = brc_push_bam_span(eng, &sp);
+                if (prc != BRC_OK) { std::fprintf(stderr, "brc_push_bam_span: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
+            }
+            fetcher.active = false;
+            brc_end_region(eng);
+            t_decode += now() - d1;
+            if (flush() != BRC_OK) { brc_destroy(eng); return 1; }
+            pushed = 0;
+            continue;
+        }
         auto push = [&](const Rec &r) {
             uint16_t lib = 0;
             if (per_lib) {

@@ -152,3 +152,22 @@ def test_region_from_compressed_span_equals_region_from_host_reads(flags):
         finally:
             e.close()
     assert texts[0] == texts[1] and len(texts[0].splitlines()) == end - beg
+
+
+@pytest.mark.gpu
+def test_cli_device_decode_matches_host_decode(tmp_path):
+    """brc-readcount with BRC_CLI_DEVICE_DECODE=1 (compressed spans -> GPU inflate/framing) prints what the host-decode path prints."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import build, synth_cb
+    exe = build.build_cli()
+    sp = synth_cb.Spec(seed=21, contig_len=1280 * 500)
+    info = synth_cb.write_sample_bam(sp, 0, 0, 500, str(tmp_path), REF_SAMTOOLS)
+    for extra in ([], ["-p", "-q", "20", "-b", "20"]):
+        args = [exe, "-w", "0"] + extra + ["-f", info["fasta"], info["bam"], "chr1:5001-600000"]
+        env = dict(os.environ, BRC_CLI_WINDOW="150000")
+        host = subprocess.run(args, capture_output=True, env=env)
+        dev = subprocess.run(args, capture_output=True, env=dict(env, BRC_CLI_DEVICE_DECODE="1"))
+        assert host.returncode == 0 and dev.returncode == 0, dev.stderr.decode()[-1500:]
+        assert dev.stdout == host.stdout and len(host.stdout.splitlines()) == 595000
