@@ -658,11 +658,65 @@ def e2e_text(cfg_name, spec, args):
             best = dt if best is None else min(best, dt)
         ref_bp = min(n_bp, 100_000)
         s, dt = _run_procs([[REF_BIN, "-w", "0"] + CONFIGS[cfg_name]["argv"] + ["-f", info["fasta"], info["bam"], f"chr1:1-{ref_bp}"]])
-        return {"value": n_bp / best, "unit": UNIT, "wall_s": best, "sample_bp": n_bp, "bam_bytes": os.path.getsize(info["bam"]),
-                "reference_one_process": s / dt, "what": "brc-readcount BAM -> text to /dev/null, one process incl. start-up; reference binary on the first "
-                f"{ref_bp} bp of the same file"}
+        out = {"value": n_bp / best, "unit": UNIT, "wall_s": best, "sample_bp": n_bp, "bam_bytes": os.path.getsize(info["bam"]),
+               "reference_one_process": s / dt, "what": "brc-readcount BAM -> text to /dev/null, one process incl. start-up; reference binary on the first "
+               f"{ref_bp} bp of the same file"}
+        try:
+            out["compressed_span"] = e2e_compressed_span(cfg_name, spec, info, n_bp)
+        except Exception as ex:
+            out["compressed_span"] = {"value": None, "error": str(ex)[:200]}
+        return out
     finally:
         shutil.rmtree(wd, ignore_errors=True)
+
+
+def e2e_compressed_span(cfg_name, spec, info, n_bp):
+    """SURVEY.md §8 f-2 end to end: the BAM's COMPRESSED BGZF blocks go to the GPU (brc_push_bam_span: inflate + framing + kernels
+    on the device), the packed records come back.  H2D = compressed bytes."""
+    import torch
+    from bam_readcount_b200 import bamio
+    from bam_readcount_b200.engine import Engine
+    hdr, _ = None, None
+    bai = bamio.BaiIndex(info["bam"] + ".bai")
+    text = subprocess.check_output([os.path.join(ROOT, "oracle", "_ref", "samtools"), "view", "-H", info["bam"]], text=True)
+    h = bamio.BamHeader(text, ["chr1"], [info["length"]])
+    rg_lib = {rg: h.lib_of_rg(rg) for rg in h.rg_lb}
+    flags = CONFIGS[cfg_name]["flags"]
+    e = Engine(lib_names=h.lib_names, **flags)
+    try:
+        e.set_reference(0, "chr1", info["length"], spec.ref_host(0, 0, info["length"]), 0)
+        win = 1_280_000
+        spans = []
+        for b in range(0, n_bp, win):
+            sp = bamio.bam_span(info["bam"], bai, 0, max(b - 1, 0), min(b + win, n_bp), rg_lib)
+            keep = torch.frombuffer(bytearray(sp["comp"]), dtype=torch.uint8).pin_memory()
+            sp["comp"] = keep.numpy()
+            spans.append((b, min(b + win, n_bp), sp, keep))
+        times, h2d, d2h = [], 0, 0
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hh = dd = 0
+            for b, en, sp, _ in spans:
+                e.reset()
+                e.begin_region(0, b, en, False)
+                e.push_bam_span(sp)
+                e.end_region()
+                e._check(e.lib.brc_compute(e.h))
+                hh += len(sp["comp"])
+                if it == 0:
+                    dd += e.packed().nbytes()
+            dt = time.perf_counter() - t0
+            if it:
+                times.append(dt)
+            else:
+                d2h = dd
+            h2d = hh
+        ms = 1000.0 * sum(times) / len(times)
+        return {"value": n_bp / (ms / 1000.0), "unit": UNIT, "ms": ms, "h2d_bytes": h2d, "d2h_bytes": d2h, "windows": len(spans),
+                "what": "compressed BGZF spans (pinned) -> brc_push_bam_span -> brc_compute; packed records back in host memory"}
+    finally:
+        e.close()
 
 
 def run_deep(args):
