@@ -664,6 +664,10 @@ __device__ __forceinline__ void site_reset(SiteState &S, const ChunkInfo &ci, in
 }
 
 __device__ __forceinline__ int2 lds_i2(const void *p) { return *reinterpret_cast<const int2 *>(p); }
+// shared-memory loads by 32-bit address: the hot loop walks the staged descriptors with one 32-bit register instead of a
+// generic 64-bit pointer plus its shared-window twin (ncu r02a: three loop values were spilled to local memory)
+__device__ __forceinline__ int2 lds64(uint32_t a) { int2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ int4 lds128(uint32_t a) { int4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 // row * n_slots + slot of the site this thread owns
 template <bool PER_LIB>
 __device__ __forceinline__ uint32_t slot_index(const PileupParams &P, const ChunkInfo &ci, const SiteState &S) {
@@ -680,39 +684,40 @@ __device__ __forceinline__ uint32_t slot_index(const PileupParams &P, const Chun
 template <bool PER_LIB, bool STAGED>
 __device__ __forceinline__ void process_chunk(const PileupParams &P, const StageBuf &sb, uint32_t (*sacc)[TILE], uint32_t (*warn)[TILE],
                                               const ChunkInfo &ci, SiteState &S, int tid) {
-    const int4 *ds = sb.desc;
-    const int4 *const ds_end = ds + (ci.r1 - ci.r0) * 5;
+    const uint32_t desc_s = smem_u32(sb.desc);                // descriptor j of the chunk sits at desc_s + 80 j
+    uint32_t da = desc_s;
+    const uint32_t da_end = desc_s + (uint32_t)(ci.r1 - ci.r0) * (uint32_t)sizeof(ReadDesc);
     const uint32_t qual_s = smem_u32(sb.qual) - ci.qbase32;   // staged bytes are addressed with the reads' low-32 pool offsets
     const uint32_t seq_s = smem_u32(sb.seq) - ci.sbase32;
-    const int32_t wfirst = S.wfirst, wlast = S.wfirst + 31;
+    const int32_t wfirst = S.wfirst;
     {   // vectorised skip of the leading reads that end before this warp's first site (32 reads per ballot):
         // keeps the 8 warps of a tile in step — the last warp would otherwise walk ~45 dead reads one by one
         const int n_in = ci.r1 - ci.r0, lane = tid & 31;
         int start = 0;
         for (; start < n_in; start += 32) {
             const int j = start + lane;
-            const int endj = j < n_in ? ds[j * 5].y : 0x7fffffff;
+            const int endj = j < n_in ? sb.desc[j * 5].y : 0x7fffffff;
             const unsigned m = __ballot_sync(0xffffffffu, endj > wfirst);
             if (m) { start += __ffs(m) - 1; break; }
         }
         if (start >= n_in) return;
-        ds += start * 5;
+        da += (uint32_t)start * (uint32_t)sizeof(ReadDesc);
     }
     uint32_t pk3 = 0u, pkmb = 0u;                                 // count | plus << 8 | nq2 << 16 ;  baseq | mapq << 16
-#ifndef BRC_K1_NO_PREFETCH
-    int2 pe_next = lds_i2(ds);                                    // software prefetch of the next read's (pos,end)
+#ifdef BRC_K1_PREFETCH
+    int2 pe_next = lds64(da);                                     // software prefetch of the next read's (pos,end)
 #endif
-    for (; ds < ds_end; ds += 5) {
-#ifndef BRC_K1_NO_PREFETCH
+    for (; da < da_end; da += (uint32_t)sizeof(ReadDesc)) {
+#ifdef BRC_K1_PREFETCH
         const int2 pe = pe_next;
-        pe_next = lds_i2(ds + 5);                                 // may run one record past the chunk: staged garbage, never used
+        pe_next = lds64(da + (uint32_t)sizeof(ReadDesc));         // may run one record past the chunk: staged garbage, never used
 #else
-        const int2 pe = lds_i2(ds);
+        const int2 pe = lds64(da);                                // pos, end
 #endif
-        if (pe.x > wlast) { S.warp_done = true; break; }          // reads are position-sorted within a region
+        if (pe.x - wfirst > 31) { S.warp_done = true; break; }    // reads are position-sorted within a region
         if (pe.y <= wfirst) continue;
         const bool cover = S.site >= pe.x && S.site < pe.y;
-        const int2 fl2 = lds_i2(&ds[0].z);                        // fm, lib_nc
+        const int2 fl2 = lds64(da + 8u);                          // fm, lib_nc
         if (PER_LIB) {
             const uint32_t lib = (uint32_t)fl2.y & 0xFFFFu;
             if (lib == LIB_NONE) { if (cover) S.flags |= 1u; continue; }
@@ -724,7 +729,7 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
         if (!cover) continue;
         S.ncover++;
         const uint32_t fm = (uint32_t)fl2.x;
-        const int4 q3 = ds[3];                                   // qual32,seq32,cig,n_cigar
+        const int4 q3 = lds128(da + 48u);                        // qual32,seq32,cig,n_cigar
         int qpos, indel = 0;
         uint32_t bq, base;
         if (fm & FM_HOT) {
@@ -732,18 +737,18 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
             if (fm & FM_DEAD) continue;
             qpos = S.site - pe.x + q3.z;
             if (STAGED) bq = lds_u8(qual_s + (uint32_t)q3.x + (uint32_t)qpos);
-            else bq = P.qual[P.qual_off[ci.r0 + (int)((ds - sb.desc) / 5)] + (uint32_t)qpos];
+            else bq = P.qual[P.qual_off[ci.r0 + (int)((da - desc_s) / (uint32_t)sizeof(ReadDesc))] + (uint32_t)qpos];
             if ((int)bq < P.min_bq) continue;
             S.npass++;
             uint32_t byte;
             if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
-            else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
+            else byte = P.seq[P.seq_off[ci.r0 + (int)((da - desc_s) / (uint32_t)sizeof(ReadDesc))] + ((uint32_t)qpos >> 1)];
             base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
             if (S.pbase == NO_BASE) S.pbase = base;
             if (base == S.pbase) {
-                const int4 q1 = ds[1];                           // mmq,clen,lclip,tpi
-                const int4 q2 = ds[2];                           // q2,nmfrac,se,fl
-                const int4 q4 = ds[4];                           // rcp_l, rcp_clen, fclen, inc
+                const int4 q1 = lds128(da + 16u);                // mmq,clen,lclip,tpi
+                const int4 q2 = lds128(da + 32u);                // q2,nmfrac,se,fl
+                const int4 q4 = lds128(da + 64u);                // rcp_l, rcp_clen, fclen, inc
                 const float fl = __int_as_float(q2.w), rcp_l = __int_as_float(q4.x);
                 const float d3 = div_small((float)abs(qpos - q1.w), fl, rcp_l);
                 const float f = div_small((float)abs(2 * (qpos - q1.z) - q1.y), __int_as_float(q4.z), __int_as_float(q4.y));
@@ -771,12 +776,12 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
             }
             if (fm & FM_DEAD) continue;                          // mapq / flag filter (R:...:288-310)
             if (STAGED) bq = lds_u8(qual_s + (uint32_t)q3.x + (uint32_t)qpos);
-            else bq = P.qual[P.qual_off[ci.r0 + (int)((ds - sb.desc) / 5)] + (uint32_t)qpos];
+            else bq = P.qual[P.qual_off[ci.r0 + (int)((da - desc_s) / (uint32_t)sizeof(ReadDesc))] + (uint32_t)qpos];
             if ((int)bq < P.min_bq) continue;
             S.npass++;
             const bool warns = (fm & (FM_NM_ABSENT | FM_SM_MISSING)) != 0;   // a tag the reference warns about is missing
             if (indel != 0) {
-                const int32_t r = ci.r0 + (int)((ds - sb.desc) / 5);
+                const int32_t r = ci.r0 + (int)((da - desc_s) / (uint32_t)sizeof(ReadDesc));
                 S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), indel > 0 ? KIND_INS : KIND_DEL, indel > 0 ? indel : -indel, r, qpos, bq, true);
                 if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
                 if (indel > 0 && P.insertion_centric) continue;
@@ -784,18 +789,18 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
             if (warns) { warn[0][tid] += (fm >> 25) & 1u; warn[1][tid] += (fm >> 26) & 1u; }
             uint32_t byte;
             if (STAGED) byte = lds_u8(seq_s + (uint32_t)q3.y + ((uint32_t)qpos >> 1));
-            else byte = P.seq[P.seq_off[ci.r0 + (int)((ds - sb.desc) / 5)] + ((uint32_t)qpos >> 1)];
+            else byte = P.seq[P.seq_off[ci.r0 + (int)((da - desc_s) / (uint32_t)sizeof(ReadDesc))] + ((uint32_t)qpos >> 1)];
             base = canonical16((byte >> ((~qpos & 1) << 2)) & 0xFu);
             if (S.pbase == NO_BASE) S.pbase = base;
         }
         // ---- an event that is not (hot, primary): full-width accumulation ----
         if (base != S.pbase && S.sbase != NO_BASE && base != S.sbase) {   // third base class at this site: rare
-            S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), (int)base, 0, ci.r0 + (int)((ds - sb.desc) / 5), qpos, bq, false);
+            S.sec_head = rare_event(P, S.sec_head, slot_index<PER_LIB>(P, ci, S), (int)base, 0, ci.r0 + (int)((da - desc_s) / (uint32_t)sizeof(ReadDesc)), qpos, bq, false);
             continue;
         }
-        const int4 q1 = ds[1];                                   // mmq,clen,lclip,tpi
-        const int4 q2 = ds[2];                                   // q2,nmfrac,se,fl
-        const int4 q4 = ds[4];                                   // rcp_l, rcp_clen, fclen
+        const int4 q1 = lds128(da + 16u);                        // mmq,clen,lclip,tpi
+        const int4 q2 = lds128(da + 32u);                        // q2,nmfrac,se,fl
+        const int4 q4 = lds128(da + 64u);                        // rcp_l, rcp_clen, fclen
         const Terms t = event_terms((fm & FM_FASTDIV) != 0, qpos, q2.x, q1.w, q1.z, q1.y, __int_as_float(q2.w), __int_as_float(q4.z),
                                     __int_as_float(q4.x), __int_as_float(q4.y));
         const bool has_q2 = q2.x > -1;

@@ -75,42 +75,53 @@ HD int ref_off(int kind, int q) {
     return q < 10 ? -1 : q - 10;
 }
 
-// bases (4-bit packed, 75 bytes) and qualities (150 bytes) of one read; returns NM
+// bases (4-bit packed, 75 bytes) and qualities (150 bytes) of one read; returns NM.
+// Everything stays in registers (no indexed local arrays): quality values come out of a packed constant, the <= 6 substitution
+// positions live in one 64-bit word and are patched into the finished row.
 HD int32_t make_body(uint64_t seed, uint64_t contig, const Hdr &h, int64_t start, uint8_t *seq, uint8_t *qual) {
-    // substitution positions (distinct) and their shifts
-    int sp[6], ss[6]; int ns = 0;
-    {
-        const uint64_t h2 = sub_stream(h.rk, 2), h3 = sub_stream(h.rk, 3);
-        for (int t = 0; t < h.n_subs; ++t) {
-            const uint64_t src = t < 3 ? h2 >> (20 * t) : h3 >> (20 * (t - 3));
-            const int p = (int)((uint32_t)(src & 0xFFFFu) % (uint32_t)RL);
-            const int s = 1 + (int)((uint32_t)((src >> 16) & 0xFu) % 3u);
-            bool dup = false;
-            for (int k = 0; k < ns; ++k) dup = dup || sp[k] == p;
-            if (!dup) { sp[ns] = p; ss[ns] = s; ++ns; }
-        }
-    }
     const uint64_t hb = sub_stream(h.rk, 4);
-    int32_t nm = h.kind == 1 ? 2 : (h.kind == 2 ? 3 : 0);
     uint64_t rw = 0; int64_t rw_idx = -1;
-    const uint8_t quals[7] = {37, 37, 37, 30, 25, 12, 2};
+    const uint64_t qtab = 0x020C191E252525ULL;                     // {37,37,37,30,25,12,2}, 8 bits each
     uint64_t hq = 0; uint32_t hi_nib = 0;
+    const int tail_from = RL - h.tail;
     for (int q = 0; q < RL; ++q) {
         if ((q & 7) == 0) hq = sub_stream(h.rk, 8 + (uint64_t)(q >> 3));
         const uint32_t qb = (uint32_t)(hq >> (8 * (q & 7))) & 0xFFu;
-        qual[q] = q >= RL - h.tail ? (uint8_t)2 : quals[(qb * 7u) >> 8];
+        qual[q] = q >= tail_from ? (uint8_t)2 : (uint8_t)(qtab >> (8 * ((qb * 7u) >> 8)));
         const int ro = ref_off(h.kind, q);
         uint32_t base;
         if (ro >= 0) {
             const int64_t p = start + ro;
             if ((p >> 5) != rw_idx) { rw_idx = p >> 5; rw = ref_word(seed, contig, (uint64_t)rw_idx); }
             base = (uint32_t)(rw >> (2 * (p & 31))) & 3u;
-            for (int k = 0; k < ns; ++k) if (sp[k] == q) { base = (base + (uint32_t)ss[k]) & 3u; ++nm; }
         } else base = (uint32_t)(hb >> (2 * (q & 31))) & 3u;
         const uint32_t nib = 1u << base;
         if (q & 1) seq[q >> 1] = (uint8_t)((hi_nib << 4) | nib); else hi_nib = nib;
     }
     if (RL & 1) seq[RL >> 1] = (uint8_t)(hi_nib << 4);
+    // substitutions: distinct positions (first occurrence wins), only on bases that came from the reference
+    int32_t nm = h.kind == 1 ? 2 : (h.kind == 2 ? 3 : 0);
+    if (h.n_subs > 0) {
+        const uint64_t h2 = sub_stream(h.rk, 2), h3 = sub_stream(h.rk, 3);
+        uint64_t seen = ~0ull;                                      // up to 6 positions, 8 bits each (0xFF = none)
+        for (int t = 0; t < 6; ++t) {
+            if (t >= h.n_subs) break;
+            const uint64_t src = t < 3 ? h2 >> (20 * t) : h3 >> (20 * (t - 3));
+            const uint32_t p = (uint32_t)(src & 0xFFFFu) % (uint32_t)RL;
+            const uint32_t sft = 1u + ((uint32_t)((src >> 16) & 0xFu) % 3u);
+            bool dup = false;
+            for (int k = 0; k < 6; ++k) dup = dup || ((uint32_t)(seen >> (8 * k)) & 0xFFu) == p;
+            if (dup) continue;
+            seen = (seen << 8) | p;
+            if (ref_off(h.kind, (int)p) < 0) continue;
+            const uint32_t byte = seq[p >> 1];
+            const uint32_t nib = (p & 1u) ? (byte & 15u) : (byte >> 4);
+            const uint32_t code = nib == 1u ? 0u : (nib == 2u ? 1u : (nib == 4u ? 2u : 3u));
+            const uint32_t nn = 1u << ((code + sft) & 3u);
+            seq[p >> 1] = (uint8_t)((p & 1u) ? ((byte & 0xF0u) | nn) : ((byte & 0x0Fu) | (nn << 4)));
+            ++nm;
+        }
+    }
     return nm;
 }
 

@@ -135,19 +135,21 @@ class WindowRunner:
         self.eng.set_reference_device(contig, f"chr{contig + 1}", L, 0, self.ref_ascii.data_ptr(), L, sp)
         self.cur_contig = contig
 
-    def launch(self, w: Window, sec_cap: int = 0):
-        """Generate window w's reads in HBM and enqueue the engine's kernels; returns immediately."""
+    def launch(self, w: Window, sec_cap: int = 0, resident=None):
+        """Enqueue the engine's kernels for window w; its reads are generated in HBM first, unless `resident` (a DeviceWindow
+        that already holds them) is given.  Returns immediately."""
         import torch
         if self.busy:
             self.done.synchronize()
             self.sent.synchronize()
         sp = self.stream.cuda_stream
         self._ensure_reference(w.contig)
-        n = self.dw.fill(w.contig, w.blk_lo, w.blk_hi, sp)
+        dw = resident if resident is not None else self.dw
+        n = dw.n_reads if resident is not None else dw.fill(w.contig, w.blk_lo, w.blk_hi, sp)
         reg = window_region(w)
         reg.read_hi = n
         self.eng.plan_device([reg], n, sec_cap)
-        self.eng.run_device(self.dw.c_batch(), None, sp)
+        self.eng.run_device(dw.c_batch(), None, sp)
         if self.n_sec_host is None:
             self.n_sec_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         pk = self.eng.device_packed()

@@ -131,7 +131,7 @@ def write_sample_bam(spec: "Spec", contig: int, lo: int, hi: int, workdir: str, 
 class DeviceWindow:
     """Device buffers for windows of up to ``max_reads`` reads (torch owns the memory)."""
 
-    def __init__(self, spec: Spec, max_reads: int, device):
+    def __init__(self, spec: Spec, max_reads: int, device, scratch=None, with_region: bool = True):
         import torch
         self.spec, self.cap = spec, int(max_reads)
         n = self.cap
@@ -139,8 +139,14 @@ class DeviceWindow:
         self.t = dict(pos=z(n, torch.int32), flag=z(n, torch.int16), mapq=z(n, torch.uint8), lib=z(n, torch.int16), l_qseq=z(n, torch.int32),
                       nm=z(n, torch.int32), sm=z(n, torch.int32), cigar_off=z(n + 1, torch.int64), cigar=z(3 * n + 16, torch.int32),
                       seq_off=z(n + 1, torch.int64), seq=z(75 * n + 64, torch.uint8), qual_off=z(n + 1, torch.int64),
-                      qual=z(150 * n + 64, torch.uint8), region=z(n, torch.int32), scratch=z(n // BLOCK_READS + 4, torch.int64))
+                      qual=z(150 * n + 64, torch.uint8), region=z(n if with_region else 1, torch.int32),
+                      scratch=scratch if scratch is not None else z(n // BLOCK_READS + 4, torch.int64))
+        self.with_region = with_region
         self.n_reads = 0
+
+    @staticmethod
+    def bytes_per_read() -> int:
+        return 4 + 2 + 1 + 2 + 4 + 4 + 4 + 8 + 12 + 8 + 75 + 8 + 150
 
     def fill(self, contig: int, lo: int, hi: int, stream_ptr: int) -> int:
         """Enqueue the generator kernels for blocks / sites [lo, hi) on the stream; returns the read count."""
@@ -148,7 +154,7 @@ class DeviceWindow:
         assert n <= self.cap, (n, self.cap)
         t = self.t
         out = COut(n, None, *[t[k].data_ptr() for k in ("pos", "flag", "mapq", "lib", "l_qseq", "nm", "sm", "cigar_off", "cigar", "seq_off",
-                                                         "seq", "qual_off", "qual")], t["region"].data_ptr())
+                                                         "seq", "qual_off", "qual")], t["region"].data_ptr() if self.with_region else None)
         rc = load().brc_synth_fill_device(C.byref(self.spec.c), contig, lo, hi, C.byref(out), t["scratch"].data_ptr(), stream_ptr)
         assert rc == 0, rc
         self.n_reads = n
