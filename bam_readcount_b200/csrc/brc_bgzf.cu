@@ -32,10 +32,12 @@ __global__ void __launch_bounds__(INFL_WARPS * 32) bgzf_inflate_kernel(const uin
     __shared__ inflate::Tables tabs[INFL_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * INFL_WARPS + warp;
-    if (b >= n_blocks || lane != 0) return;          // the DEFLATE symbol stream is inherently serial: one lane decodes, the block-level parallelism fills the GPU
+    if (b >= n_blocks) return;
+    // the DEFLATE symbol stream is serial: all 32 lanes run the decoder in lockstep (the cost of one), lane 0 writes tables and
+    // literals, the warp copies matches together; block-level parallelism fills the GPU
     const BlockEnt e = blocks[b];
-    const int rc = e.isize ? inflate::inflate_block(comp + e.cdata_off, e.clen, U + e.uoff, e.isize, tabs[warp]) : 0;
-    if (rc != 0) atomicMin(status, rc);
+    const int rc = e.isize ? inflate::inflate_block(inflate::Lanes{lane, 32}, comp + e.cdata_off, e.clen, U + e.uoff, e.isize, tabs[warp]) : 0;
+    if (rc != 0 && lane == 0) atomicMin(status, rc);
 }
 
 __device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }

@@ -1,12 +1,16 @@
 // brc_bgzf.cuh — DEFLATE (RFC 1951) decoder core shared by the device kernel of brc_bgzf.cu and its host twin.
 //
 // BGZF blocks are independent raw-DEFLATE streams of <= 64 KiB (V:htslib-1.10/bgzf.c:697 inflate_block,
-// :897 bgzf_read_block), so a BAM file inflates block-parallel.  One decoder instance = one block: a bit reader over the
-// compressed bytes, canonical-Huffman tables (a 10-bit / 9-bit primary table, the canonical count/symbol arrays as the
-// slow path for longer codes — the formulation of zlib's contrib/puff), and the literal/match loop.  Written once as
-// __host__ __device__ code so the exact instruction sequence the GPU runs is unit-tested on the CPU against zlib.
+// :897 bgzf_read_block), so a BAM file inflates block-parallel.  One decoder instance = one block = one WARP: the symbol stream
+// is serial, so every lane runs the decoder redundantly and in lockstep (same registers, same control flow — it costs the issue
+// slots of one lane), which makes the warp-wide steps natural: lane 0 alone writes the Huffman tables and the literals, all
+// lanes copy a match / a stored run together.  On the host the same code runs with one lane, so the exact instruction
+// sequence the GPU executes is unit-tested on the CPU against zlib (tests/test_bgzf_device.py).
+// Tables: a 10-bit / 9-bit primary lookup (symbol << 4 | length), the canonical count/symbol arrays (the formulation of zlib's
+// contrib/puff) as the slow path for longer codes.
 #pragma once
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define BRC_HD __host__ __device__ __forceinline__
@@ -28,13 +32,36 @@ struct Tables {                     // per decoder: 2048 + 1024 + 640 + 64 ... b
     uint8_t lens[32 + FIXLCODES + MAXDCODES + 2];   // scratch: code lengths while a header is read
 };
 
-struct Bits {
-    const uint8_t *p, *end;
+// the lanes of one decoder: 32 on the device, 1 on the host
+struct Lanes {
+    int lane, n;
+    BRC_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
+};
+
+struct Bits {                       // LSB-first bit reader over `n` bytes at `base`; 4 bytes per refill once aligned
+    const uint8_t *base; int64_t n, pos;
     uint64_t buf; int cnt;
     bool overrun;
 };
-BRC_HD void bits_init(Bits &b, const uint8_t *p, int64_t n) { b.p = p; b.end = p + n; b.buf = 0; b.cnt = 0; b.overrun = false; }
-BRC_HD void bits_refill(Bits &b) { while (b.cnt <= 56 && b.p < b.end) { b.buf |= (uint64_t)(*b.p++) << b.cnt; b.cnt += 8; } }
+BRC_HD void bits_init(Bits &b, const uint8_t *p, int64_t n) { b.base = p; b.n = n; b.pos = 0; b.buf = 0; b.cnt = 0; b.overrun = false; }
+BRC_HD void bits_refill(Bits &b) {
+    while (b.cnt <= 32 && b.pos < b.n) {
+        const uint8_t *p = b.base + b.pos;
+        if (b.pos + 4 <= b.n && (reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
+            uint32_t w;
+#if defined(__CUDA_ARCH__)
+            w = *reinterpret_cast<const uint32_t *>(p);
+#else
+            std::memcpy(&w, p, 4);
+#endif
+            b.buf |= (uint64_t)w << b.cnt; b.cnt += 32; b.pos += 4;
+        } else { b.buf |= (uint64_t)(*p) << b.cnt; b.cnt += 8; b.pos += 1; }
+    }
+}
 // try to have n (<= 32) bits buffered; near the end of the stream fewer may be left (the missing high bits read as zeros) —
 // CONSUMING more bits than the stream holds raises `overrun`
 BRC_HD void bits_need(Bits &b, int n) { if (b.cnt < n) bits_refill(b); }
@@ -70,6 +97,14 @@ BRC_HD int build(uint16_t *count, uint16_t *symtab, uint16_t *primary, int pbits
     return left;
 }
 
+// lane 0 builds (it writes the tables), everybody learns the verdict
+BRC_HD int build_shared(const Lanes &L, uint16_t *count, uint16_t *symtab, uint16_t *primary, int pbits, const uint8_t *length, int n, int *verdict) {
+    L.sync();
+    if (L.lane == 0) *verdict = build(count, symtab, primary, pbits, length, n);
+    L.sync();
+    return *verdict;
+}
+
 // one symbol: primary table, else the canonical walk over the longer lengths (bit by bit, MSB-first codes in an LSB-first stream)
 BRC_HD int decode(Bits &b, const uint16_t *count, const uint16_t *symtab, const uint16_t *primary, int pbits) {
     bits_need(b, MAXBITS);
@@ -86,84 +121,92 @@ BRC_HD int decode(Bits &b, const uint16_t *count, const uint16_t *symtab, const 
     return -1;
 }
 
-BRC_HD void fixed_lengths(uint8_t *lens) {
-    int s = 0;
-    for (; s < 144; ++s) lens[s] = 8;
-    for (; s < 256; ++s) lens[s] = 9;
-    for (; s < 280; ++s) lens[s] = 7;
-    for (; s < FIXLCODES; ++s) lens[s] = 8;
-    for (int d = 0; d < MAXDCODES; ++d) lens[FIXLCODES + d] = 5;
-}
-
 // Inflates one raw-DEFLATE stream of `clen` bytes into out[0 .. isize).  Returns 0 on success, a negative code otherwise.
-// Single-threaded by construction (the device kernel runs it in one lane of a warp; see brc_bgzf.cu).
-BRC_HD int inflate_block(const uint8_t *in, int64_t clen, uint8_t *out, uint32_t isize, Tables &T) {
+// Every lane of L calls it with the same arguments and gets the same return value.
+BRC_HD int inflate_block(const Lanes &L, const uint8_t *in, int64_t clen, uint8_t *out, uint32_t isize, Tables &T) {
     // length / distance code -> (base, extra bits) by formula (RFC 1951 §3.2.5), no tables in local memory:
     //   length   sym < 8: 3 + sym, 0;   sym == 28: 258, 0;   else e = (sym - 4) >> 2, ((4 + (sym & 3)) << e) + 3
     //   distance d < 4: d + 1, 0;       else e = (d - 2) >> 1, ((2 + (d & 1)) << e) + 1
     // order of the code-length code lengths (§3.2.7), 5 bits each: 16 17 18 0 8 7 9 6 10 5 11 4 | 12 3 13 2 14 1 15
     const uint64_t order_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 | 10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
     const uint64_t order_hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+    int *verdict = reinterpret_cast<int *>(T.lens + 28);          // 4 bytes of the scratch nobody else uses (lens[19..32) is free)
     Bits b; bits_init(b, in, clen);
     uint32_t o = 0;
     int last = 0;
+    bool fixed_ready = false;
     while (!last) {
         last = (int)bits_get(b, 1);
         const uint32_t type = bits_get(b, 2);
         if (type == 0) {                               // stored: back to the byte stream
             if (b.overrun) return -17;
             bits_drop(b, b.cnt & 7);
-            b.p -= b.cnt >> 3; b.cnt = 0; b.buf = 0;    // the buffered whole bytes were real stream bytes: hand them back
-            if (b.end - b.p < 4) return -19;
-            const uint32_t len = b.p[0] | (b.p[1] << 8), nlen = b.p[2] | (b.p[3] << 8);
-            b.p += 4;
-            if ((len ^ 0xFFFFu) != nlen || (int64_t)len > b.end - b.p || o + len > isize) return -20;
-            for (uint32_t k = 0; k < len; ++k) out[o + k] = b.p[k];
-            o += len; b.p += len;
+            b.pos -= b.cnt >> 3; b.cnt = 0; b.buf = 0;  // the buffered whole bytes were real stream bytes: hand them back
+            if (b.n - b.pos < 4) return -19;
+            const uint8_t *p = b.base + b.pos;
+            const uint32_t len = p[0] | (p[1] << 8), nlen = p[2] | (p[3] << 8);
+            b.pos += 4;
+            if ((len ^ 0xFFFFu) != nlen || (int64_t)len > b.n - b.pos || o + len > isize) return -20;
+            p += 4;
+            for (uint32_t k = (uint32_t)L.lane; k < len; k += (uint32_t)L.n) out[o + k] = p[k];
+            o += len; b.pos += len;
             continue;
         }
         if (type == 3) return -2;
         if (type == 1) {
-            fixed_lengths(T.lens);
-            build(T.lcount, T.lsym, T.lit, LIT_BITS, T.lens, FIXLCODES);
-            build(T.dcount, T.dsym, T.dist, DIST_BITS, T.lens + FIXLCODES, MAXDCODES);
+            if (!fixed_ready) {
+                L.sync();                               // nobody still reads the previous block's tables
+                if (L.lane == 0) {
+                    int s = 0;
+                    for (; s < 144; ++s) T.lens[32 + s] = 8;
+                    for (; s < 256; ++s) T.lens[32 + s] = 9;
+                    for (; s < 280; ++s) T.lens[32 + s] = 7;
+                    for (; s < FIXLCODES; ++s) T.lens[32 + s] = 8;
+                    for (int d = 0; d < MAXDCODES; ++d) T.lens[32 + FIXLCODES + d] = 5;
+                }
+                build_shared(L, T.lcount, T.lsym, T.lit, LIT_BITS, T.lens + 32, FIXLCODES, verdict);
+                build_shared(L, T.dcount, T.dsym, T.dist, DIST_BITS, T.lens + 32 + FIXLCODES, MAXDCODES, verdict);
+                fixed_ready = true;
+            }
         } else {
+            fixed_ready = false;
             const int nlen = (int)bits_get(b, 5) + 257, ndist = (int)bits_get(b, 5) + 1, ncode = (int)bits_get(b, 4) + 4;
             if (nlen > MAXLCODES || ndist > MAXDCODES) return -3;
-            int idx = 0;
-            for (; idx < 19; ++idx) {
+            L.sync();                                   // nobody still reads the previous block's tables
+            for (int idx = 0; idx < 19; ++idx) {
                 const int pos = (int)((idx < 12 ? order_lo >> (5 * idx) : order_hi >> (5 * (idx - 12))) & 31u);
-                T.lens[pos] = idx < ncode ? (uint8_t)bits_get(b, 3) : (uint8_t)0;
+                const uint32_t v = idx < ncode ? bits_get(b, 3) : 0u;
+                if (L.lane == 0) T.lens[pos] = (uint8_t)v;
             }
-            // the code-length code: 19 symbols, lengths <= 7; reuse the literal arrays as its table (7-bit primary inside lit[])
-            if (build(T.lcount, T.lsym, T.lit, 7, T.lens, 19) != 0) return -4;
-            // its lengths live in lens[0..19): the code lengths being read go to lens[32 ...] then move down
-            uint8_t *cl = T.lens + 32;
-            idx = 0;
+            // the code-length code: 19 symbols, lengths <= 7; the literal arrays hold its table for now (7-bit primary inside lit[])
+            if (build_shared(L, T.lcount, T.lsym, T.lit, 7, T.lens, 19, verdict) != 0) return -4;
+            uint8_t *cl = T.lens + 32;                  // the code lengths being read
+            int idx = 0, prev = 0;
             while (idx < nlen + ndist) {
                 const int sym = decode(b, T.lcount, T.lsym, T.lit, 7);
                 if (sym < 0) return -5;
-                if (sym < 16) cl[idx++] = (uint8_t)sym;
+                if (sym < 16) { if (L.lane == 0) cl[idx] = (uint8_t)sym; ++idx; prev = sym; }
                 else {
                     int len = 0, rep;
-                    if (sym == 16) { if (idx == 0) return -6; len = cl[idx - 1]; rep = 3 + (int)bits_get(b, 2); }
+                    if (sym == 16) { if (idx == 0) return -6; len = prev; rep = 3 + (int)bits_get(b, 2); }
                     else if (sym == 17) rep = 3 + (int)bits_get(b, 3);
                     else rep = 11 + (int)bits_get(b, 7);
                     if (idx + rep > nlen + ndist) return -7;
-                    while (rep--) cl[idx++] = (uint8_t)len;
+                    if (L.lane == 0) for (int k = 0; k < rep; ++k) cl[idx + k] = (uint8_t)len;
+                    idx += rep; prev = len;
                 }
             }
+            L.sync();
             if (cl[256] == 0) return -8;               // no end-of-block code
-            int err = build(T.lcount, T.lsym, T.lit, LIT_BITS, cl, nlen);
+            int err = build_shared(L, T.lcount, T.lsym, T.lit, LIT_BITS, cl, nlen, verdict);
             if (err < 0 || (err > 0 && nlen - T.lcount[0] != 1)) return -9;
-            // distance lengths follow the literal lengths; copy them out of the way of nothing: build reads them in place
-            err = build(T.dcount, T.dsym, T.dist, DIST_BITS, cl + nlen, ndist);
+            err = build_shared(L, T.dcount, T.dsym, T.dist, DIST_BITS, cl + nlen, ndist, verdict);
             if (err < 0 || (err > 0 && ndist - T.dcount[0] != 1)) return -11;
         }
         for (;;) {
             int sym = decode(b, T.lcount, T.lsym, T.lit, LIT_BITS);
             if (sym < 0) return -12;
-            if (sym < 256) { if (o >= isize) return -13; out[o++] = (uint8_t)sym; continue; }
+            if (sym < 256) { if (o >= isize) return -13; if (L.lane == 0) out[o] = (uint8_t)sym; ++o; continue; }
             if (sym == 256) break;
             sym -= 257;
             if (sym >= 29) return -14;
@@ -174,9 +217,12 @@ BRC_HD int inflate_block(const uint8_t *in, int64_t clen, uint8_t *out, uint32_t
             const int de = ds < 4 ? 0 : (ds - 2) >> 1;
             const uint32_t dist = (ds < 4 ? (uint32_t)ds + 1u : (((2u + ((uint32_t)ds & 1u)) << de) + 1u)) + (de ? bits_get(b, de) : 0u);
             if (dist > o || o + len > isize) return -16;
+            // the whole warp copies the match: byte k of it is byte (k mod dist) of the `dist` bytes before it (LZ77 replication)
             const uint8_t *src = out + (o - dist);
             uint8_t *dst = out + o;
-            for (uint32_t k = 0; k < len; ++k) dst[k] = src[k];      // overlapping copies replicate, byte order matters
+            L.sync();                                   // the literals lane 0 stored are visible to the other lanes
+            for (uint32_t k = (uint32_t)L.lane; k < len; k += (uint32_t)L.n) dst[k] = src[dist >= len ? k : k % dist];
+            L.sync();
             o += len;
         }
     }

@@ -38,10 +38,10 @@ int main(int argc, char **argv) {
             std::vector<uint8_t> want(isize + 1), got(isize + 1);
             z_stream zs{}; inflateInit2(&zs, -15); zs.next_in = (Bytef *)h + hdr; zs.avail_in = total - hdr - 8; zs.next_out = want.data(); zs.avail_out = isize;
             int rc = inflate(&zs, Z_FINISH); inflateEnd(&zs);
-            int r = brc::inflate::inflate_block(h + hdr, total - hdr - 8, got.data(), isize, T);
+            int r = brc::inflate::inflate_block(brc::inflate::Lanes{0, 1}, h + hdr, total - hdr - 8, got.data(), isize, T);
             if (r != 0 || memcmp(want.data(), got.data(), isize) || (isize && rc != Z_STREAM_END)) ++bad;
             // a truncated stream must be refused, not over-read
-            if (isize > 100 && brc::inflate::inflate_block(h + hdr, (total - hdr - 8) / 2, got.data(), isize, T) == 0) ++bad;
+            if (isize > 100 && brc::inflate::inflate_block(brc::inflate::Lanes{0, 1}, h + hdr, (total - hdr - 8) / 2, got.data(), isize, T) == 0) ++bad;
             ++nblk; o += total;
         }
     }
