@@ -89,6 +89,7 @@ void brc_destroy(brc_engine *e) {
     for (auto &ev : e->pipe_ev) if (ev) cudaEventDestroy(ev);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
+    if (e->s_sec) cudaStreamDestroy(e->s_sec);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -472,7 +473,7 @@ static int run_kernels(brc_engine *e, const int32_t *d_region_of_read, cudaStrea
     return BRC_OK;
 }
 
-static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetched = false) {
+static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetched = false, int64_t sec_done = 0) {
     const int64_t rs = (int64_t)e->n_rows * e->n_slots;
     int32_t cnt = 0;
     CU(cudaMemcpyAsync(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost, s), "D2H sec_count");
@@ -483,7 +484,9 @@ static int fetch_results(brc_engine *e, cudaStream_t s, bool slots_already_fetch
     CU(e->h_words.reserve(rs1 * 4 * N_WORDS), "pin"); CU(e->h_sec.reserve((size_t)ns1 * sizeof(SecRec)), "pin");
     CU(e->h_misc.reserve(64), "pin");
     if (rs && !slots_already_fetched) CU(cudaMemcpyAsync(e->h_words.p, e->d_words.p, rs * 4 * N_WORDS, cudaMemcpyDeviceToHost, s), "D2H words");
-    if (cnt) CU(cudaMemcpyAsync(e->h_sec.p, e->d_sec.p, (size_t)cnt * sizeof(SecRec), cudaMemcpyDeviceToHost, s), "D2H sec");
+    if (cnt > sec_done)      // records [0, sec_done) were copied while the kernels ran (compute_pipelined)
+        CU(cudaMemcpyAsync((char *)e->h_sec.p + (size_t)sec_done * sizeof(SecRec), (char *)e->d_sec.p + (size_t)sec_done * sizeof(SecRec),
+                           (size_t)(cnt - sec_done) * sizeof(SecRec), cudaMemcpyDeviceToHost, s), "D2H sec");
     CU(cudaMemcpyAsync(e->h_misc.p, e->d_warn.p, 16, cudaMemcpyDeviceToHost, s), "D2H warn");
     CU(cudaStreamSynchronize(s), "sync D2H");
     const unsigned long long *w = e->h_misc.as<unsigned long long>();
@@ -573,7 +576,7 @@ static int issue_h2d_chunks(brc_engine *e) {
     int n_chunks = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)(in_bytes >> 26)));   // ~64 MiB of input per chunk
     n_chunks = (int)std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 4096));
     if (const char *ov = std::getenv("BRC_PIPE_CHUNKS")) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::atoi(ov), std::max<int64_t>(1, n)));   // test hook
-    while (e->pipe_ev.size() < (size_t)(2 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
+    while (e->pipe_ev.size() < (size_t)(3 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
     if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, e->s_in), "memset lib");
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
@@ -609,6 +612,11 @@ static int compute_pipelined(brc_engine *e) {
     // host result buffers
     const int64_t rs1 = std::max<int64_t>(rs, 1);
     CU(e->h_words.reserve(rs1 * 4 * N_WORDS), "pin");
+    CU(e->h_sec.reserve((size_t)e->sec_cap * sizeof(SecRec)), "pin");          // pool records leave while the kernels run
+    CU(e->h_misc.reserve(64 + 4 * 64), "pin");
+    if (!e->s_sec) CU(cudaStreamCreateWithFlags(&e->s_sec, cudaStreamNonBlocking), "stream");
+    int32_t *h_cnt = e->h_misc.as<int32_t>() + 16;                              // pool counter after each chunk's kernels
+    std::vector<int> cnt_chunks;
 
     PrecomputeParams P0; PileupParams P1;
     make_params(e, nullptr, P0, P1);
@@ -634,6 +642,11 @@ static int compute_pipelined(brc_engine *e) {
             CU(launch_pileup(P1, sk), "launch pileup"); e->launch_count++;
             CU(launch_deep_sites(P1, sk), "launch deep_sites"); if (P1.n_deep) e->launch_count++;
             CU(cudaEventRecord(e->pipe_ev[2 * c + 1], sk), "event");
+            if (c < 64) {   // snapshot of the pool counter: the records allocated so far are final (a tile is computed by exactly one launch)
+                CU(cudaMemcpyAsync(h_cnt + c, P1.res.sec_count, 4, cudaMemcpyDeviceToHost, sk), "D2H pool counter");
+                CU(cudaEventRecord(e->pipe_ev[2 * n_chunks + 2 + (int)cnt_chunks.size()], sk), "event");
+                cnt_chunks.push_back(c);
+            }
             // ---- D2H of the finished slots ----
             CU(cudaStreamWaitEvent(e->s_out, e->pipe_ev[2 * c + 1], 0), "wait");
             const int64_t s0 = e->tiles[(size_t)tile_done].slot0;
@@ -649,6 +662,18 @@ static int compute_pipelined(brc_engine *e) {
     const double t1 = wall_ms();
     CU(cudaEventRecord(e->ev[1], sk), "event");
     CU(cudaEventRecord(e->ev[2], sk), "event");
+    // everything is queued: follow the kernels and ship the pool records each chunk finished (their own stream: the word copies
+    // of later chunks are already queued on s_out)
+    int64_t sec_done = 0;
+    for (size_t k = 0; k + 1 < cnt_chunks.size(); ++k) {     // the last chunk's records go with fetch_results
+        CU(cudaEventSynchronize(e->pipe_ev[2 * n_chunks + 2 + (int)k]), "sync pool counter");
+        const int64_t cur = std::min<int64_t>(h_cnt[cnt_chunks[k]], e->sec_cap);
+        if (cur > sec_done) {
+            CU(cudaMemcpyAsync((char *)e->h_sec.p + (size_t)sec_done * sizeof(SecRec), (char *)e->d_sec.p + (size_t)sec_done * sizeof(SecRec),
+                               (size_t)(cur - sec_done) * sizeof(SecRec), cudaMemcpyDeviceToHost, e->s_sec), "D2H sec (chunk)");
+            sec_done = cur;
+        }
+    }
     CU(cudaStreamSynchronize(e->s_in), "sync H2D");
     const double t2 = wall_ms();
     CU(cudaStreamSynchronize(sk), "sync kernels");
@@ -660,8 +685,9 @@ static int compute_pipelined(brc_engine *e) {
     CU(cudaMemcpy(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost), "D2H sec_count");
     e->h_n_sec = cnt;
     e->h2d_chunks = 0;
+    CU(cudaStreamSynchronize(e->s_sec), "sync D2H sec");
     if ((int64_t)cnt > e->sec_cap) return BRC_E_OVERFLOW;
-    return fetch_results(e, sk, true);
+    return fetch_results(e, sk, true, sec_done);
 }
 
 extern "C" {
