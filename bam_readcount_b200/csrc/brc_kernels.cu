@@ -613,7 +613,7 @@ struct __align__(16) ChunkInfo {
     uint32_t row, cbase32;
 };
 struct __align__(128) StageBuf {
-    int4 desc[STAGE_READS * 5];
+    int4 desc[(STAGE_READS + 1) * 5];   // + the sentinel the producer writes behind the chunk's last descriptor
     uint8_t qual[STAGE_QUAL];
     uint8_t seq[STAGE_SEQ];
     uint32_t cigar[STAGE_CIGAR];
@@ -686,7 +686,6 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
                                               const ChunkInfo &ci, SiteState &S, int tid) {
     const uint32_t desc_s = smem_u32(sb.desc);                // descriptor j of the chunk sits at desc_s + 80 j
     uint32_t da = desc_s;
-    const uint32_t da_end = desc_s + (uint32_t)(ci.r1 - ci.r0) * (uint32_t)sizeof(ReadDesc);
     const uint32_t qual_s = smem_u32(sb.qual) - ci.qbase32;   // staged bytes are addressed with the reads' low-32 pool offsets
     const uint32_t seq_s = smem_u32(sb.seq) - ci.sbase32;
     const int32_t wfirst = S.wfirst;
@@ -707,14 +706,15 @@ __device__ __forceinline__ void process_chunk(const PileupParams &P, const Stage
 #ifdef BRC_K1_PREFETCH
     int2 pe_next = lds64(da);                                     // software prefetch of the next read's (pos,end)
 #endif
-    for (; da < da_end; da += (uint32_t)sizeof(ReadDesc)) {
+    // no loop bound: the producer wrote a sentinel descriptor (pos = INT_MAX) behind the chunk's last read
+    for (;; da += (uint32_t)sizeof(ReadDesc)) {
 #ifdef BRC_K1_PREFETCH
         const int2 pe = pe_next;
         pe_next = lds64(da + (uint32_t)sizeof(ReadDesc));         // may run one record past the chunk: staged garbage, never used
 #else
         const int2 pe = lds64(da);                                // pos, end
 #endif
-        if (pe.x - wfirst > 31) { S.warp_done = true; break; }    // reads are position-sorted within a region
+        if (pe.x - wfirst > 31) { if (pe.x != 0x7fffffff) S.warp_done = true; break; }   // reads are position-sorted within a region; INT_MAX = end of chunk
         if (pe.y <= wfirst) continue;
         const bool cover = S.site >= pe.x && S.site < pe.y;
         const int2 fl2 = lds64(da + 8u);                          // fm, lib_nc
@@ -962,6 +962,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
                     ci.r0 = r0; ci.r1 = r1;
                     ci.flags |= (first ? 2u : 0u) | (r1 >= hi ? 4u : 0u) | (narrow ? 8u : 0u);
                     sm.info[s] = ci;
+                    sm.st[s].desc[(r1 - r0) * 5] = make_int4(0x7fffffff, 0x7fffffff, 0, 0);   // sentinel (pos, end): released to the consumers by the arrive below
                     mbar_expect_tx(&sm.full[s], bytes);
                     tma_bulk_g2s(sm.st[s].desc, P.desc + r0, db, &sm.full[s]);
                     if (qbytes) tma_bulk_g2s(sm.st[s].qual, P.qual + qa, qbytes, &sm.full[s]);
@@ -990,7 +991,11 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
 #ifdef BRC_K1_PROFILE
         const long long tc0 = clock64();
 #endif
-        mbar_wait_hint<200>(&sm.full[s], ph);
+#ifdef BRC_K1_HINT_WAIT
+        mbar_wait_relaxed(&sm.full[s], ph);          // try_wait with a suspend-time hint: the warp sleeps on the barrier instead of polling
+#else
+        mbar_wait_hint<200>(&sm.full[s], ph);        // ncu r02a: this poll loop is 8 % of the issued instructions but 2 % of the stall samples
+#endif
 #ifdef BRC_K1_PROFILE
         const long long tc1 = clock64();
 #endif
