@@ -26,6 +26,7 @@
 // shortcuts of the hot loop (reciprocal division for small integers, float<->double by bit
 // casts) are exact and checked against the IEEE intrinsics by brc_selftest_fastmath.
 #include <algorithm>
+#include <cstdlib>
 
 #include "brc_device.cuh"
 
@@ -1042,7 +1043,12 @@ cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
     }
     const int sms = dev < 64 && g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
     const int64_t n_work = p.tile_count * (int64_t)p.res.n_rows;
-    const unsigned grid = (unsigned)std::min<int64_t>(n_work, (int64_t)sms * BRC_K1_CTAS_PER_SM);   // persistent CTAs
+    // persistent CTAs, 3 per SM.  A multi-GPU caller whose NCCL send/recv kernels must run NEXT to this kernel (the ordered-emit
+    // gather, bam_readcount_b200/stream.py) leaves a few CTA slots free with BRC_K1_RESERVE_CTAS: a grid that fills every slot
+    // makes the collective wait for the tail of each launch (r02m2: 2-GPU step 483 ms against 348 ms of compute)
+    static const int reserve = std::getenv("BRC_K1_RESERVE_CTAS") ? std::max(0, std::atoi(std::getenv("BRC_K1_RESERVE_CTAS"))) : 0;
+    const int64_t slots = std::max<int64_t>((int64_t)sms * BRC_K1_CTAS_PER_SM - reserve, sms);
+    const unsigned grid = (unsigned)std::min<int64_t>(n_work, slots);
     const size_t smem = sizeof(PileupSmem);
     if (p.per_lib) pileup_kernel<true><<<grid, K1_THREADS, smem, s>>>(p);
     else pileup_kernel<false><<<grid, K1_THREADS, smem, s>>>(p);

@@ -356,6 +356,7 @@ def run_wgs(args, cfg_name):
     numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        os.environ.setdefault("BRC_K1_RESERVE_CTAS", str(args.reserve_ctas))     # room for the NCCL kernels of the gather next to K1
     spec = make_spec(cfg_name, args)
     flags = cfg["flags"]
     resident = cfg_name == "c3"
@@ -617,6 +618,7 @@ def run_wgs(args, cfg_name):
                        "window_events": w_events, "window_keys": w_keys, "window_packed_result_bytes": packed_bytes,
                        "l2": "every window's inputs (%.0f MB) exceed the 126 MB L2; no flush" % (alg_bytes / 1e6),
                        "gather": (None if world == 1 else {"transport": "NCCL send/recv of the packed records to rank 0, one group per round",
+                                                           "k1_reserved_cta_slots": int(os.environ.get("BRC_K1_RESERVE_CTAS", "0")),
                                                            "rounds_per_step": rounds, "bytes_to_rank0_per_step": ring.bytes_received / max(args.steps + args.warmup, 1),
                                                            "verified_checksums": gather_ok}),
                        "numa": numa},
@@ -931,6 +933,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-text", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--reserve-ctas", type=int, default=32, help="N > 1: CTA slots pileup_kernel leaves free for the NCCL kernels of the gather")
     ap.add_argument("--no-resident", action="store_true", help="c4: regenerate every window inside the timed loop instead of keeping windows in HBM")
     ap.add_argument("--hbm-margin-gb", type=float, default=14.0, help="HBM left free when windows are kept resident")
     args = ap.parse_args()

@@ -242,3 +242,34 @@ def test_empty_batches_and_reuse_of_one_handle():
             assert eng.format_text() == want
     finally:
         eng.close()
+
+
+def test_carried_deletion_queue_equals_one_batch():
+    """brc_set_queue_carry: argv regions flushed one per brc_compute (what brc-readcount does to bound its memory) print exactly
+    what the same regions print as ONE batch — the reference's never-cleared deletion queue (R:bamreadcount.cpp:650-656) travels
+    with the engine — and exactly what the reference binary printed (golden edge_alleles_*)."""
+    import edge_cases
+    from bam_readcount_b200.engine import Engine
+    case = edge_cases.multi_allele_case()
+    for fl_name, fl in case["flag_sets"].items():
+        one, _, _, _ = cases.run_engine(case, fl, site_list=False, want_dump=False)
+        e = Engine(lib_names=case["lib_names"], **fl)
+        try:
+            name, clen, seq, wb = case["contigs"][0]
+            e.set_reference(0, name, clen, seq, wb)
+            assert e.lib.brc_set_queue_carry(e.h, 1) == 0
+            parts = []
+            for (ci, b1, e1) in case["regions"]:
+                tid, beg, end, sub = cases.region_reads(case, ci, b1, e1)
+                e.reset()
+                e.begin_region(tid, beg, end, False)
+                e.push_reads(sub)
+                e.end_region()
+                e.compute()
+                parts.append(e.format_text(-1))
+            assert "".join(parts) == one, fl_name
+            # carry off again: a fresh queue per call
+            assert e.lib.brc_set_queue_carry(e.h, 0) == 0
+        finally:
+            e.close()
+        assert one == cases.load_golden_text(f"edge_alleles_{fl_name}.txt")
