@@ -87,6 +87,7 @@ void brc_destroy(brc_engine *e) {
     for (auto *b : pins) b->release();
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->pipe_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->tm_ev) if (ev) cudaEventDestroy(ev);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->s_sec) cudaStreamDestroy(e->s_sec);
@@ -579,23 +580,28 @@ static int issue_h2d_chunks(brc_engine *e) {
     n_chunks = (int)std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 4096));
     if (const char *ov = std::getenv("BRC_PIPE_CHUNKS")) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::atoi(ov), std::max<int64_t>(1, n)));   // test hook
     while (e->pipe_ev.size() < (size_t)(4 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
-    if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, e->s_in2), "memset lib");
+    const bool two_streams = std::getenv("BRC_H2D_TWO_STREAMS") != nullptr;
+    const bool tm = std::getenv("BRC_PIPE_TIMING") != nullptr;
+    if (tm) { for (auto &ev : e->tm_ev) if (!ev) CU(cudaEventCreate(&ev), "event"); CU(cudaEventRecord(e->tm_ev[0], e->s_in), "event"); }
+    if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, two_streams ? e->s_in2 : e->s_in), "memset lib");
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
-        // two copy streams: the two big byte pools on one, the eleven small arrays on the other — a single stream leaves the link
-        // idle between the many short copies (r02c: 34.7 GB/s in flight against 49 GB/s for plain copies on the same box)
+        // one copy stream by default.  (BRC_H2D_TWO_STREAMS=1 puts the eleven small arrays on a second stream; measured SLOWER on
+        // B200 / PCIe Gen5: 21.0 vs 18.9 ms per 10 Mb window, r02m2b — kept as a switch for other hosts.)
+        cudaStream_t s_small = two_streams ? e->s_in2 : e->s_in;
         #define H2D(st, k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, st), "H2D chunk")
         H2D(e->s_in, 12, B.qual, B.qual_off[a], B.qual_off[b] - B.qual_off[a], 1);
         H2D(e->s_in, 10, B.seq, B.seq_off[a], B.seq_off[b] - B.seq_off[a], 1);
-        H2D(e->s_in2, 0, B.pos, a, b - a, 4); H2D(e->s_in2, 1, B.flag, a, b - a, 2); H2D(e->s_in2, 2, B.mapq, a, b - a, 1);
-        if (B.lib) H2D(e->s_in2, 3, B.lib, a, b - a, 2);
-        H2D(e->s_in2, 4, B.l_qseq, a, b - a, 4); H2D(e->s_in2, 5, B.nm, a, b - a, 4); H2D(e->s_in2, 6, B.sm, a, b - a, 4);
-        H2D(e->s_in2, 7, B.cigar_off, a, b - a + 1, 8); H2D(e->s_in2, 8, B.cigar, B.cigar_off[a], B.cigar_off[b] - B.cigar_off[a], 4);
-        H2D(e->s_in2, 9, B.seq_off, a, b - a + 1, 8); H2D(e->s_in2, 11, B.qual_off, a, b - a + 1, 8);
+        H2D(s_small, 0, B.pos, a, b - a, 4); H2D(s_small, 1, B.flag, a, b - a, 2); H2D(s_small, 2, B.mapq, a, b - a, 1);
+        if (B.lib) H2D(s_small, 3, B.lib, a, b - a, 2);
+        H2D(s_small, 4, B.l_qseq, a, b - a, 4); H2D(s_small, 5, B.nm, a, b - a, 4); H2D(s_small, 6, B.sm, a, b - a, 4);
+        H2D(s_small, 7, B.cigar_off, a, b - a + 1, 8); H2D(s_small, 8, B.cigar, B.cigar_off[a], B.cigar_off[b] - B.cigar_off[a], 4);
+        H2D(s_small, 9, B.seq_off, a, b - a + 1, 8); H2D(s_small, 11, B.qual_off, a, b - a + 1, 8);
         #undef H2D
         CU(cudaEventRecord(e->pipe_ev[2 * c], e->s_in), "event");
         CU(cudaEventRecord(e->pipe_ev[3 * n_chunks + 2 + c], e->s_in2), "event");
     }
+    if (tm) CU(cudaEventRecord(e->tm_ev[1], e->s_in), "event");
     e->h2d_chunks = n_chunks;
     return BRC_OK;
 }
@@ -656,6 +662,7 @@ static int compute_pipelined(brc_engine *e) {
             }
             // ---- D2H of the finished slots ----
             CU(cudaStreamWaitEvent(e->s_out, e->pipe_ev[2 * c + 1], 0), "wait");
+            if (timing && tile_done == 0) CU(cudaEventRecord(e->tm_ev[2], e->s_out), "event");
             const int64_t s0 = e->tiles[(size_t)tile_done].slot0;
             const int64_t s1 = tile_to < n_tiles ? e->tiles[(size_t)tile_to].slot0 : e->n_slots;
             const size_t w = (size_t)(s1 - s0);
@@ -688,6 +695,12 @@ static int compute_pipelined(brc_engine *e) {
     const double t3 = wall_ms();
     CU(cudaStreamSynchronize(e->s_out), "sync D2H");
     const double t4 = wall_ms();
+    if (timing) {
+        float h2d_ms = 0, d2h_ms = 0, lag_ms = 0;
+        cudaEventRecord(e->tm_ev[3], e->s_out); cudaEventSynchronize(e->tm_ev[3]);
+        cudaEventElapsedTime(&h2d_ms, e->tm_ev[0], e->tm_ev[1]); cudaEventElapsedTime(&d2h_ms, e->tm_ev[2], e->tm_ev[3]); cudaEventElapsedTime(&lag_ms, e->tm_ev[0], e->tm_ev[2]);
+        std::fprintf(stderr, "[brc pipe] device clocks: H2D stream busy %.2f ms, first D2H starts +%.2f ms after the first H2D, D2H span %.2f ms\n", h2d_ms, lag_ms, d2h_ms);
+    }
     if (timing) std::fprintf(stderr, "[brc pipe] chunks %d  enqueue %.2f ms  H2D done +%.2f  kernels done +%.2f  D2H done +%.2f (ms since compute start)\n", n_chunks, t1 - t0, t2 - t0, t3 - t0, t4 - t0);
     int32_t cnt = 0;
     CU(cudaMemcpy(&cnt, e->d_sec_count.p, 4, cudaMemcpyDeviceToHost), "D2H sec_count");

@@ -355,8 +355,16 @@ def run_wgs(args, cfg_name):
     device = torch.device("cuda", local)
     numa = bind_to_gpu_numa(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-        os.environ.setdefault("BRC_K1_RESERVE_CTAS", str(args.reserve_ctas))     # room for the NCCL kernels of the gather next to K1
+        # the gather's send/recv kernels run on NCCL's own stream: make it a HIGH-PRIORITY stream, so that its CTAs are placed as
+        # soon as a pileup launch drains instead of queueing behind the next window's persistent grid
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+            dist.init_process_group("nccl", device_id=device, pg_options=opts)
+        except Exception:
+            dist.init_process_group("nccl", device_id=device)
+        if args.reserve_ctas > 0:
+            os.environ.setdefault("BRC_K1_RESERVE_CTAS", str(args.reserve_ctas))
     spec = make_spec(cfg_name, args)
     flags = cfg["flags"]
     resident = cfg_name == "c3"
@@ -476,6 +484,22 @@ def run_wgs(args, cfg_name):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    # one more pass WITHOUT the gather (untimed for `value`): what the ordered emit costs the step
+    nogather_ms = None
+    if world > 1:
+        saved_world = world
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record()
+        world = 1
+        try:
+            one_pass()
+        finally:
+            world = saved_world
+        join_streams()
+        c1.record()
+        barrier()
+        nogather_ms = c0.elapsed_time(c1)
     n_my_sites = sum(w.n_sites for w in my_windows)
     per_window_launches = 3 + runners[0].eng.launch_count()     # generator (count, scan, fill) + engine kernels
     launches = len(my_windows) * args.steps * (runners[0].eng.launch_count() if resident else per_window_launches)
@@ -578,7 +602,7 @@ def run_wgs(args, cfg_name):
         e2e = dict(ms=1000.0 * sum(times) / len(times), sites=sites, h2d=h2d, d2h=d2h_per, windows=ne)
 
     # ---- reduce over ranks: max time, sum of units ----
-    t = torch.tensor([elapsed_ms, e2e["ms"] if e2e else 0.0], device=device, dtype=torch.float64)
+    t = torch.tensor([elapsed_ms, e2e["ms"] if e2e else 0.0, nogather_ms or 0.0], device=device, dtype=torch.float64)
     u = torch.tensor([n_my_sites, e2e["sites"] if e2e else 0, e2e["h2d"] if e2e else 0, e2e["d2h"] if e2e else 0, launches,
                       1 if parity.get("identical", True) else 0], device=device, dtype=torch.float64)
     if world > 1:
@@ -620,7 +644,9 @@ def run_wgs(args, cfg_name):
                        "gather": (None if world == 1 else {"transport": "NCCL send/recv of the packed records to rank 0, one group per round",
                                                            "k1_reserved_cta_slots": int(os.environ.get("BRC_K1_RESERVE_CTAS", "0")),
                                                            "rounds_per_step": rounds, "bytes_to_rank0_per_step": ring.bytes_received / max(args.steps + args.warmup, 1),
-                                                           "verified_checksums": gather_ok}),
+                                                           "verified_checksums": gather_ok,
+                                                           "ms_per_step_without_gather": float(t[2]),
+                                                           "positions_per_s_without_gather": tot_sites / (float(t[2]) / 1000.0) if float(t[2]) > 0 else None}),
                        "numa": numa},
             "roofline": {"bound": "hbm", "kernel": "pileup_kernel (K1), one window", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -933,7 +959,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-text", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--reserve-ctas", type=int, default=32, help="N > 1: CTA slots pileup_kernel leaves free for the NCCL kernels of the gather")
+    ap.add_argument("--reserve-ctas", type=int, default=0, help="N > 1: CTA slots pileup_kernel leaves free for the NCCL kernels of the gather")
     ap.add_argument("--no-resident", action="store_true", help="c4: regenerate every window inside the timed loop instead of keeping windows in HBM")
     ap.add_argument("--hbm-margin-gb", type=float, default=14.0, help="HBM left free when windows are kept resident")
     args = ap.parse_args()
