@@ -160,6 +160,15 @@ class WindowRunner:
             self.sent.record(self.stream)
         self.window, self.busy = w, True
 
+    def packed_tensors_fixed(self, sec_cap_records: int):
+        """(words, sec[:cap], count) aliasing the engine's device records WITHOUT waiting for the window: every size is known from
+        the window's geometry, so a gather can be queued behind the kernels (stream order) with no host synchronisation."""
+        pk = self.eng.device_packed()
+        rs = int(pk.n_rows) * int(pk.n_slots)
+        cap = min(int(sec_cap_records), int(pk.n_sec))
+        return (alias_device_bytes(pk.words, rs * 4 * N_WORDS, self.device), alias_device_bytes(pk.sec, cap * SEC_RECORD_BYTES, self.device),
+                alias_device_bytes(pk.sec_count, 4, self.device))
+
     def packed_tensors(self):
         """(words bytes, sec bytes) aliasing the engine's device records of the finished window (call after done)."""
         pk = self.eng.device_packed()
@@ -190,6 +199,33 @@ class GatherRing:
                 self.spool_s[src] = torch.empty(max_sec_bytes, dtype=torch.uint8, device=device)
         self.bytes_received = 0
         self.rounds = 0
+
+    def round_fixed(self, mine, peers):
+        """Size-exchange-free round: `mine` = (words, sec[:cap], count4) uint8 device tensors of this rank's window or None;
+        `peers` (rank 0 only) = {src: (words_bytes, sec_bytes)} of what each peer sends this round (known from the shard plan).
+        Nothing here waits on the host: the ops are queued on the current stream behind the kernels that produce the data."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        ops, got = [], []
+        if self.rank == 0:
+            for src, (nw, ns) in sorted(peers.items()):
+                if nw > self.spool_w[src].numel() or ns + 4 > self.spool_s[src].numel():
+                    raise RuntimeError(f"gather spool too small for rank {src}: {nw}/{ns} bytes")
+                tw, ts, tc = self.spool_w[src][:nw], self.spool_s[src][:ns], self.spool_s[src][ns:ns + 4]
+                ops += [dist.P2POp(dist.irecv, tw, src, group=self.group), dist.P2POp(dist.irecv, ts, src, group=self.group),
+                        dist.P2POp(dist.irecv, tc, src, group=self.group)]
+                got.append((src, tw, ts))
+                self.bytes_received += nw + ns + 4
+        elif mine is not None:
+            ops = [dist.P2POp(dist.isend, t, 0, group=self.group) for t in mine]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if self.rank == 0 and self.consume is not None:
+            for src, tw, ts in got:
+                self.consume(src, tw, ts)
+        self.rounds += 1
 
     def round(self, words, sec):
         """words / sec: uint8 device tensors of this rank's finished window (empty tensors when it has none this round).

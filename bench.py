@@ -416,26 +416,38 @@ def run_wgs(args, cfg_name):
 
     ring = st.GatherRing(rank, world, device, max_slots * 4 * N_WORDS, (max_slots // 3 + 8192) * SEC_RECORD_BYTES, consume=consume) if world > 1 else None
 
+    # records per pool message: a fixed bound from the window's geometry (25 % above what this workload needs), so that a round
+    # needs no size exchange and no host synchronisation; the true count travels with it and is checked after the pass
+    def sec_msg_records(w):
+        return int(w.n_slots * args.sec_msg_per_site) + 4096
+
     def gather_round(j, verify):
         run = runners[j % n_runners] if j < len(my_windows) else None
         with torch.cuda.stream(comm):
+            mine = None
             if run is not None:
-                run.done.synchronize()
-                comm.wait_event(run.done)
-                tw, ts = run.packed_tensors()
+                comm.wait_event(run.done)                 # stream order only: the host does not wait for the window
+                mine = run.packed_tensors_fixed(sec_msg_records(my_windows[j]))
                 if verify and rank > 0:
                     sp = comm.cuda_stream
-                    synth_cb.checksum_device(tw, acc[world + rank:world + rank + 1], sp)
-                    if ts.numel():
-                        synth_cb.checksum_device(ts, acc[world + rank:world + rank + 1], sp)
-            else:
-                tw = ts = torch.empty(0, dtype=torch.uint8, device=device)
-            ring.round(tw, ts)
+                    synth_cb.checksum_device(mine[0], acc[world + rank:world + rank + 1], sp)
+                    synth_cb.checksum_device(mine[1], acc[world + rank:world + rank + 1], sp)
+            peers = {}
+            if rank == 0:
+                for src in range(1, world):
+                    a0, b0 = shards[src]
+                    if resident:
+                        a0, b0 = src, src + 1
+                    if a0 + j < b0:
+                        wj = all_windows[a0 + j]
+                        rsj = wj.n_slots * (len(LIBS) if flags.get("per_lib") else 1)
+                        peers[src] = (rsj * 4 * N_WORDS, min(sec_msg_records(wj), rsj // 4 + 4096) * SEC_RECORD_BYTES)
+            ring.round_fixed(mine, peers)
             if run is not None:
                 run.sent.record(comm)
 
     def one_pass(verify=False):
-        lag = n_runners - 1
+        lag = 0            # the gather of window k is queued right behind its kernels (stream order; no host wait)
         for k in range(rounds + (lag if world > 1 else 0)):
             if k < len(my_windows):
                 if resident and runners[0].window is not None:
@@ -484,6 +496,11 @@ def run_wgs(args, cfg_name):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    gather_overflow = 0
+    if world > 1:
+        for r_ in runners:
+            if r_.window is not None and r_.n_sec_host is not None and int(r_.n_sec_host[0]) > sec_msg_records(r_.window):
+                gather_overflow += 1
     # one more pass WITHOUT the gather (untimed for `value`): what the ordered emit costs the step
     nogather_ms = None
     if world > 1:
@@ -644,7 +661,8 @@ def run_wgs(args, cfg_name):
                        "gather": (None if world == 1 else {"transport": "NCCL send/recv of the packed records to rank 0, one group per round",
                                                            "k1_reserved_cta_slots": int(os.environ.get("BRC_K1_RESERVE_CTAS", "0")),
                                                            "rounds_per_step": rounds, "bytes_to_rank0_per_step": ring.bytes_received / max(args.steps + args.warmup, 1),
-                                                           "verified_checksums": gather_ok,
+                                                           "verified_checksums": gather_ok, "pool_message_records_per_site": args.sec_msg_per_site,
+                                                           "pool_message_overflows_rank0": gather_overflow,
                                                            "ms_per_step_without_gather": float(t[2]),
                                                            "positions_per_s_without_gather": tot_sites / (float(t[2]) / 1000.0) if float(t[2]) > 0 else None}),
                        "numa": numa},
@@ -959,6 +977,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-text", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sec-msg-per-site", type=float, default=0.19, help="gather: pool records sent per site slot (fixed message size; C4 needs 0.152)")
     ap.add_argument("--reserve-ctas", type=int, default=0, help="N > 1: CTA slots pileup_kernel leaves free for the NCCL kernels of the gather")
     ap.add_argument("--no-resident", action="store_true", help="c4: regenerate every window inside the timed loop instead of keeping windows in HBM")
     ap.add_argument("--hbm-margin-gb", type=float, default=14.0, help="HBM left free when windows are kept resident")
