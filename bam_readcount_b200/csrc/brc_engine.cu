@@ -668,7 +668,11 @@ static int compute_pipelined(brc_engine *e) {
             const size_t w = (size_t)(s1 - s0);
             const size_t pitch4 = (size_t)e->n_slots * 4;
             const int rows = e->n_rows;
-            // the finished slots of all N_WORDS x rows word arrays: one strided copy
+            // the finished slots of all N_WORDS x rows word arrays: one strided copy (or, BRC_D2H_1D=1, one plain copy per array)
+            if (std::getenv("BRC_D2H_1D") && rows * N_WORDS <= 64) {
+                for (int k = 0; k < rows * N_WORDS; ++k)
+                    CU(cudaMemcpyAsync((char *)e->h_words.p + (size_t)k * pitch4 + s0 * 4, (char *)e->d_words.p + (size_t)k * pitch4 + s0 * 4, w * 4, cudaMemcpyDeviceToHost, e->s_out), "D2H");
+            } else
             CU(cudaMemcpy2DAsync((char *)e->h_words.p + s0 * 4, pitch4, (char *)e->d_words.p + s0 * 4, pitch4, w * 4, (size_t)rows * N_WORDS, cudaMemcpyDeviceToHost, e->s_out), "D2H");
             tile_done = tile_to;
         }

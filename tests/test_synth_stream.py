@@ -145,6 +145,17 @@ def _gather_worker(rank, world, port, q):
         ts = torch.from_numpy(rng.integers(0, 256, ns, dtype=np.uint8))
         sent.append((tw, ts))
         ring.round(tw, ts)
+    # the size-exchange-free protocol (fixed message sizes known from the shard plan): words, pool bound, 4-byte count
+    fixed_sent = []
+    for k in range(2):
+        nw, ns = 64 * (k + 1), 144
+        mine = None
+        if rank == 1:
+            mine = (torch.from_numpy(rng.integers(0, 256, nw, dtype=np.uint8)), torch.from_numpy(rng.integers(0, 256, ns, dtype=np.uint8)),
+                    torch.from_numpy(np.array([k + 1], dtype=np.int32).view(np.uint8).copy()))
+            fixed_sent.append((mine[0], mine[1]))
+        ring.round_fixed(mine, {1: (nw, ns)} if rank == 0 else {})
+    sent += fixed_sent
     q.put((rank, [(s, a.numpy().tobytes(), b.numpy().tobytes()) for s, a, b in got], [(a.numpy().tobytes(), b.numpy().tobytes()) for a, b in sent]))
     dist.barrier()
     dist.destroy_process_group()
@@ -167,7 +178,7 @@ def test_gather_ring_two_ranks_gloo():
         assert p.exitcode == 0
     got0, _ = res[0]
     _, sent1 = res[1]
-    assert [g[0] for g in got0] == [1, 1, 1]
+    assert [g[0] for g in got0] == [1, 1, 1, 1, 1]
     assert [(g[1], g[2]) for g in got0] == sent1          # rank 0 received rank 1's records, round by round, byte for byte
     assert res[1][0] == []
 
