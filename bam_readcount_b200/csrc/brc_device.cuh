@@ -203,6 +203,8 @@ cudaError_t launch_precompute(const PrecomputeParams &p, cudaStream_t s);
 cudaError_t launch_ref_encode(const char *d_ascii, uint8_t *d_code, int64_t n, cudaStream_t s);
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s);
 cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s);   // no-op when p.n_deep == 0
+cudaError_t launch_fill_offsets(uint64_t *off, int64_t n, uint64_t base, uint64_t stride, cudaStream_t s);   // off[i] = base + i * stride
+cudaError_t launch_fill_i32(int32_t *dst, int64_t n, int32_t v, cudaStream_t s);
 cudaError_t launch_fastmath_selftest(int max_b, unsigned long long *d_bad, cudaStream_t s);
 
 }  // namespace brc

@@ -262,7 +262,11 @@ static int issue_h2d_chunks(brc_engine *e);
 // Parallel scan of a batch: are all reads admitted by the pileup buffer as they are (so the batch can be used in
 // place), and what is the largest bam_endpos?  The -d rule cannot fire when the whole batch is smaller than max_cnt.
 static double wall_ms_fwd() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-struct BatchScan { bool ok = true; int64_t max_end = 0; int64_t indel_ops = 0; };
+struct BatchScan {
+    bool ok = true; int64_t max_end = 0; int64_t indel_ops = 0;
+    // arrays the device can rebuild instead of receiving (fixed-length reads): offsets that are arithmetic, constant columns
+    bool reg_seq = true, reg_qual = true, const_lq = true, const_sm = true;
+};
 static BatchScan scan_batch(const brc_read_batch *b, int32_t rtid, int per_lib, int n_rows) {
     const int64_t n = b->n_reads;
     unsigned hw = std::thread::hardware_concurrency();
@@ -271,7 +275,14 @@ static BatchScan scan_batch(const brc_read_batch *b, int32_t rtid, int per_lib, 
     auto work = [&](int t) {
         const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
         BatchScan r;
+        const uint64_t s0 = b->seq_off[0], q0 = b->qual_off[0];
+        const uint64_t ks = n ? b->seq_off[1] - s0 : 0, kq = n ? b->qual_off[1] - q0 : 0;
+        const int32_t lq0 = n ? b->l_qseq[0] : 0, sm0 = n ? b->sm[0] : 0;
         for (int64_t i = lo; i < hi && r.ok; ++i) {
+            r.reg_seq = r.reg_seq && b->seq_off[i + 1] - s0 == (uint64_t)(i + 1) * ks;
+            r.reg_qual = r.reg_qual && b->qual_off[i + 1] - q0 == (uint64_t)(i + 1) * kq;
+            r.const_lq = r.const_lq && b->l_qseq[i] == lq0;
+            r.const_sm = r.const_sm && b->sm[i] == sm0;
             if ((b->tid && b->tid[i] != rtid) || (b->flag[i] & 4)) { r.ok = false; break; }
             if (i > 0 && b->pos[i] < b->pos[i - 1]) { r.ok = false; break; }
             if (per_lib && b->lib && b->lib[i] != BRC_LIB_NONE && (int)b->lib[i] >= n_rows) { r.ok = false; break; }
@@ -293,7 +304,10 @@ static BatchScan scan_batch(const brc_read_batch *b, int32_t rtid, int per_lib, 
     work(0);
     for (auto &x : th) x.join();
     BatchScan out;
-    for (auto &r : part) { out.ok = out.ok && r.ok; out.max_end = std::max(out.max_end, r.max_end); out.indel_ops += r.indel_ops; }
+    for (auto &r : part) {
+        out.ok = out.ok && r.ok; out.max_end = std::max(out.max_end, r.max_end); out.indel_ops += r.indel_ops;
+        out.reg_seq = out.reg_seq && r.reg_seq; out.reg_qual = out.reg_qual && r.reg_qual; out.const_lq = out.const_lq && r.const_lq; out.const_sm = out.const_sm && r.const_sm;
+    }
     return out;
 }
 
@@ -312,12 +326,14 @@ int brc_push_reads(brc_engine *e, const brc_read_batch *b) {
         // Optional (BRC_EARLY_H2D=1): start the copies before the admission scan.  Measured on B200/PCIe Gen5 it is SLOWER end to end
         // (28.9 vs 23.2 ms): the uploads run ahead alone and the result download then has the link to itself at the end, instead of
         // both directions streaming concurrently for the whole step — so the default issues H2D from brc_compute.
-        e->borrowed = *b; e->h2d_chunks = 0;
+        e->borrowed = *b; e->h2d_chunks = 0; e->skip_h2d = 0;
         cudaSetDevice(e->cfg.device);
         const bool early = std::getenv("BRC_EARLY_H2D") && issue_h2d_chunks(e) == BRC_OK;
         const BatchScan sc = scan_batch(b, rtid, e->cfg.per_lib, e->n_rows);
         if (std::getenv("BRC_PIPE_TIMING")) std::fprintf(stderr, "[brc pipe] scan_batch %.2f ms\n", wall_ms_fwd() - tp0);
         if (sc.ok) {
+            e->skip_h2d = (sc.reg_seq ? 1 : 0) | (sc.reg_qual ? 2 : 0) | (sc.const_lq ? 4 : 0) | (sc.const_sm ? 8 : 0);
+            if (std::getenv("BRC_NO_H2D_ELISION") || b->n_reads < 2) e->skip_h2d = 0;
             e->is_borrowed = true; e->borrowed = *b;
             e->n_indel_ops += sc.indel_ops;
             if (sc.max_end > e->open_max_end) e->open_max_end = sc.max_end;
@@ -581,26 +597,39 @@ static int issue_h2d_chunks(brc_engine *e) {
     if (const char *ov = std::getenv("BRC_PIPE_CHUNKS")) n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::atoi(ov), std::max<int64_t>(1, n)));   // test hook
     while (e->pipe_ev.size() < (size_t)(4 * n_chunks + 2)) { cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event"); e->pipe_ev.push_back(ev); }
     const bool two_streams = std::getenv("BRC_H2D_TWO_STREAMS") != nullptr;
+    // fixed-length reads: arithmetic offsets and constant columns are rebuilt on the device instead of crossing PCIe
+    // (24 of the 277 bytes a 150 bp read costs: brc_push_reads' admission scan found them regular)
+    const int skip = e->skip_h2d;
+    if (skip & 1) CU(launch_fill_offsets(e->d_in[9].as<uint64_t>(), n + 1, B.seq_off[0], B.seq_off[1] - B.seq_off[0], e->s_in), "fill seq_off");
+    if (skip & 2) CU(launch_fill_offsets(e->d_in[11].as<uint64_t>(), n + 1, B.qual_off[0], B.qual_off[1] - B.qual_off[0], e->s_in), "fill qual_off");
+    if (skip & 4) CU(launch_fill_i32(e->d_in[4].as<int32_t>(), n, B.l_qseq[0], e->s_in), "fill l_qseq");
+    if (skip & 8) CU(launch_fill_i32(e->d_in[6].as<int32_t>(), n, B.sm[0], e->s_in), "fill sm");
     const bool tm = std::getenv("BRC_PIPE_TIMING") != nullptr;
     if (tm) { for (auto &ev : e->tm_ev) if (!ev) CU(cudaEventCreate(&ev), "event"); CU(cudaEventRecord(e->tm_ev[0], e->s_in), "event"); }
     if (!B.lib) CU(cudaMemsetAsync(e->d_in[3].p, 0, (size_t)n * 2, two_streams ? e->s_in2 : e->s_in), "memset lib");
+    // Copy order (r02e, B200 / PCIe Gen5): a cudaMemcpyAsync of a megabyte or less costs ~50 us of link time whatever its size, so
+    // the eleven small arrays are sent WHOLE, once (<= 11 copies), and only the two big byte pools are cut into chunks that the
+    // kernels and the result copies follow; 13 arrays x 8 chunks ran the link at 35 GB/s, this order at > 45 GB/s.
+    #define H2D(st, k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, st), "H2D")
+    {
+        cudaStream_t s_small = two_streams ? e->s_in2 : e->s_in;
+        H2D(s_small, 0, B.pos, 0, n, 4); H2D(s_small, 1, B.flag, 0, n, 2); H2D(s_small, 2, B.mapq, 0, n, 1);
+        if (B.lib) H2D(s_small, 3, B.lib, 0, n, 2);
+        if (!(skip & 4)) H2D(s_small, 4, B.l_qseq, 0, n, 4);
+        H2D(s_small, 5, B.nm, 0, n, 4);
+        if (!(skip & 8)) H2D(s_small, 6, B.sm, 0, n, 4);
+        H2D(s_small, 7, B.cigar_off, 0, n + 1, 8); H2D(s_small, 8, B.cigar, B.cigar_off[0], B.cigar_off[n] - B.cigar_off[0], 4);
+        if (!(skip & 1)) H2D(s_small, 9, B.seq_off, 0, n + 1, 8);
+        if (!(skip & 2)) H2D(s_small, 11, B.qual_off, 0, n + 1, 8);
+        for (int c = 0; c < n_chunks; ++c) CU(cudaEventRecord(e->pipe_ev[3 * n_chunks + 2 + c], s_small), "event");   // (two-stream switch: every chunk waits for them)
+    }
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
-        // one copy stream by default.  (BRC_H2D_TWO_STREAMS=1 puts the eleven small arrays on a second stream; measured SLOWER on
-        // B200 / PCIe Gen5: 21.0 vs 18.9 ms per 10 Mb window, r02m2b — kept as a switch for other hosts.)
-        cudaStream_t s_small = two_streams ? e->s_in2 : e->s_in;
-        #define H2D(st, k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, st), "H2D chunk")
         H2D(e->s_in, 12, B.qual, B.qual_off[a], B.qual_off[b] - B.qual_off[a], 1);
         H2D(e->s_in, 10, B.seq, B.seq_off[a], B.seq_off[b] - B.seq_off[a], 1);
-        H2D(s_small, 0, B.pos, a, b - a, 4); H2D(s_small, 1, B.flag, a, b - a, 2); H2D(s_small, 2, B.mapq, a, b - a, 1);
-        if (B.lib) H2D(s_small, 3, B.lib, a, b - a, 2);
-        H2D(s_small, 4, B.l_qseq, a, b - a, 4); H2D(s_small, 5, B.nm, a, b - a, 4); H2D(s_small, 6, B.sm, a, b - a, 4);
-        H2D(s_small, 7, B.cigar_off, a, b - a + 1, 8); H2D(s_small, 8, B.cigar, B.cigar_off[a], B.cigar_off[b] - B.cigar_off[a], 4);
-        H2D(s_small, 9, B.seq_off, a, b - a + 1, 8); H2D(s_small, 11, B.qual_off, a, b - a + 1, 8);
-        #undef H2D
         CU(cudaEventRecord(e->pipe_ev[2 * c], e->s_in), "event");
-        CU(cudaEventRecord(e->pipe_ev[3 * n_chunks + 2 + c], e->s_in2), "event");
     }
+    #undef H2D
     if (tm) CU(cudaEventRecord(e->tm_ev[1], e->s_in), "event");
     e->h2d_chunks = n_chunks;
     return BRC_OK;
@@ -668,8 +697,8 @@ static int compute_pipelined(brc_engine *e) {
             const size_t w = (size_t)(s1 - s0);
             const size_t pitch4 = (size_t)e->n_slots * 4;
             const int rows = e->n_rows;
-            // the finished slots of all N_WORDS x rows word arrays: one strided copy (or, BRC_D2H_1D=1, one plain copy per array)
-            if (std::getenv("BRC_D2H_1D") && rows * N_WORDS <= 64) {
+            // the finished slots of all N_WORDS x rows word arrays: one plain copy per array (one strided 2-D copy for many library rows)
+            if (!std::getenv("BRC_D2H_2D") && rows * N_WORDS <= 64) {      // plain copies beat one strided 2-D copy (r02e: 17.0 vs 18.4 ms per window)
                 for (int k = 0; k < rows * N_WORDS; ++k)
                     CU(cudaMemcpyAsync((char *)e->h_words.p + (size_t)k * pitch4 + s0 * 4, (char *)e->d_words.p + (size_t)k * pitch4 + s0 * 4, w * 4, cudaMemcpyDeviceToHost, e->s_out), "D2H");
             } else

@@ -109,6 +109,26 @@ cudaError_t launch_ref_encode(const char *d_ascii, uint8_t *d_code, int64_t n, c
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// columns of a batch of fixed-length reads the device rebuilds instead of receiving over PCIe (brc_engine.cu, push path)
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_offsets_kernel(uint64_t *off, int64_t n, uint64_t base, uint64_t stride) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) off[i] = base + (uint64_t)i * stride;
+}
+__global__ void fill_i32_kernel(int32_t *dst, int64_t n, int32_t v) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+cudaError_t launch_fill_offsets(uint64_t *off, int64_t n, uint64_t base, uint64_t stride, cudaStream_t s) {
+    if (n > 0) fill_offsets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(off, n, base, stride);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill_i32(int32_t *dst, int64_t n, int32_t v, cudaStream_t s) {
+    if (n > 0) fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, n, v);
+    return cudaGetLastError();
+}
+
 // --- mbarrier / bulk-TMA primitives (PTX; SASS: SYNCS.*, UBLKCP) ---
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

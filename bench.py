@@ -203,7 +203,9 @@ def reference_measure(cfg_name, args, steps, warmup, size_steps=None):
         r1 = s1 / t1
         sa, ta = rs.step(slices, cal)
         r_all = sa / ta
-        eff = int(max(1, min(slices, round(r_all / r1))))
+        # processes to run: the cgroup CPU quota when there is one (the lease's real core count), else the measured speed-up of
+        # `slices` concurrent processes over one
+        eff = int(max(1, min(slices, int(quota)))) if quota else int(max(1, min(slices, round(r_all / r1))))
         for _ in range(warmup):
             rs.step(eff, cal)
         tot_s, tot_t = 0, 0.0
