@@ -610,7 +610,8 @@ static int issue_h2d_chunks(brc_engine *e) {
     // Copy order (r02e, B200 / PCIe Gen5): a cudaMemcpyAsync of a megabyte or less costs ~50 us of link time whatever its size, so
     // the eleven small arrays are sent WHOLE, once (<= 11 copies), and only the two big byte pools are cut into chunks that the
     // kernels and the result copies follow; 13 arrays x 8 chunks ran the link at 35 GB/s, this order at > 45 GB/s.
-    #define H2D(st, k, host, off, cnt, esz) if ((cnt) > 0) CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, st), "H2D")
+    e->h2d_bytes_last = 0;
+    #define H2D(st, k, host, off, cnt, esz) if ((cnt) > 0) { e->h2d_bytes_last += (int64_t)(cnt) * (int64_t)(esz); CU(cudaMemcpyAsync((char *)e->d_in[k].p + (size_t)(off) * (esz), (const char *)(host) + (size_t)(off) * (esz), (size_t)(cnt) * (esz), cudaMemcpyHostToDevice, st), "H2D"); }
     {
         cudaStream_t s_small = two_streams ? e->s_in2 : e->s_in;
         H2D(s_small, 0, B.pos, 0, n, 4); H2D(s_small, 1, B.flag, 0, n, 2); H2D(s_small, 2, B.mapq, 0, n, 1);
@@ -824,8 +825,10 @@ int brc_compute(brc_engine *e) {
     const size_t bytes[14] = {(size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 2, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
                               (size_t)(n + 1) * 8, (size_t)n_cig * 4, (size_t)(n + 1) * 8, (size_t)n_seq, (size_t)(n + 1) * 8,
                               (size_t)n_qual, bw ? (size_t)0 : (size_t)n * 4};
+    e->h2d_bytes_last = 0;
     for (int k = 0; k < 14; ++k) {
         CU(e->d_in[k].reserve(bytes[k] + 16), "cudaMalloc(reads)");
+        e->h2d_bytes_last += (int64_t)bytes[k];
         if (bytes[k]) CU(cudaMemcpyAsync(e->d_in[k].p, src[k], bytes[k], cudaMemcpyHostToDevice, s), "H2D reads");
     }
     ReadsDev &R = e->dev_reads;
@@ -948,6 +951,8 @@ int64_t brc_selftest_fastmath(brc_engine *e, int32_t max_b) {
     if (ce != cudaSuccess) return set_cuda_error(e, ce, "fastmath selftest");
     return (int64_t)h_bad;
 }
+int64_t brc_last_h2d_bytes(const brc_engine *e) { return e ? e->h2d_bytes_last : 0; }
+
 float brc_last_stage_ms(const brc_engine *e, int stage) {
     if (!e || stage < 0 || stage > 2) return 0.0f;
     // events were recorded on the launching stream around K0 and K1; wait for the last one

@@ -92,6 +92,7 @@ struct brc_engine {
     cudaStream_t s_in = nullptr, s_in2 = nullptr, s_out = nullptr, s_sec = nullptr;   // copy streams of the pipelined push path (reads in, words out, pool records out)
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t tm_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // BRC_PIPE_TIMING: H2D first/last, D2H first/last (timing-enabled)
+    int64_t h2d_bytes_last = 0;      // bytes the last push path actually sent over PCIe (after the elision below)
     int skip_h2d = 0;                // borrowed batch: bit0 seq_off, bit1 qual_off arithmetic; bit2 l_qseq, bit3 sm constant -> rebuilt on the device
     int h2d_chunks = 0;              // >0: the borrowed batch's H2D copies are already in flight on s_in (issued by brc_push_reads)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

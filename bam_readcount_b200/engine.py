@@ -82,7 +82,7 @@ EXPORTS = [
     "brc_abi_version", "brc_create", "brc_destroy", "brc_last_error", "brc_strerror", "brc_set_reference", "brc_set_reference_device", "brc_reset",
     "brc_begin_region", "brc_push_read", "brc_push_reads", "brc_end_region", "brc_decode_bam_span", "brc_push_bam_span", "brc_fetch_decoded_batch", "brc_compute", "brc_get_results",
     "brc_get_warning_counts", "brc_format_text", "brc_format_window", "brc_write_text", "brc_set_queue_carry", "brc_plan_device", "brc_run_device", "brc_device_packed_results", "brc_get_packed_results",
-    "brc_fetch_device_results", "brc_last_launch_count", "brc_last_stage_ms", "brc_selftest_fastmath",
+    "brc_fetch_device_results", "brc_last_launch_count", "brc_last_h2d_bytes", "brc_last_stage_ms", "brc_selftest_fastmath",
 ]
 
 _lib = None
@@ -134,6 +134,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.brc_selftest_fastmath.argtypes = [C.c_void_p, C.c_int32]
     lib.brc_selftest_fastmath.restype = C.c_int64
     lib.brc_last_launch_count.argtypes = [C.c_void_p]
+    lib.brc_last_h2d_bytes.argtypes = [C.c_void_p]
+    lib.brc_last_h2d_bytes.restype = C.c_int64
     lib.brc_last_stage_ms.argtypes = [C.c_void_p, C.c_int]
     lib.brc_last_stage_ms.restype = C.c_float
     if path is None:
@@ -465,6 +467,10 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.brc_last_launch_count(self.h))
+
+    def h2d_bytes(self) -> int:
+        """Bytes the last compute() of pushed host reads copied host->device."""
+        return int(self.lib.brc_last_h2d_bytes(self.h))
 
 
 def admitted(batch: ReadBatch, tid: int, max_cnt: int) -> np.ndarray:

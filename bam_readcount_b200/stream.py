@@ -192,13 +192,49 @@ class GatherRing:
         self.rank, self.world, self.device, self.group, self.consume = rank, world, device, group, consume
         self.sizes = torch.zeros(2, dtype=torch.int64, device=device)
         self.all_sizes = torch.zeros(2 * world, dtype=torch.int64, device=device)
+        # rank 0: TWO spool sets per source, alternating by round, and a stream of its own for the emitter: the receives of
+        # round k+1 land while round k is still being consumed, so the NVLink ingress never idles behind the consumer
         self.spool_w, self.spool_s = {}, {}
-        if rank == 0:
+        self.emit_stream = None
+        self.arrived, self.consumed = [], []
+        if rank == 0 and world > 1:
             for src in range(1, world):
-                self.spool_w[src] = torch.empty(max_words_bytes, dtype=torch.uint8, device=device)
-                self.spool_s[src] = torch.empty(max_sec_bytes, dtype=torch.uint8, device=device)
+                self.spool_w[src] = [torch.empty(max_words_bytes, dtype=torch.uint8, device=device) for _ in range(2)]
+                self.spool_s[src] = [torch.empty(max_sec_bytes, dtype=torch.uint8, device=device) for _ in range(2)]
+            if torch.device(device).type == "cuda":     # (the gloo tests run the same protocol on CPU tensors: consumed inline)
+                self.emit_stream = torch.cuda.Stream(device=device)
+                self.arrived = [torch.cuda.Event() for _ in range(2)]
+                self.consumed = [torch.cuda.Event() for _ in range(2)]
+                for ev in self.consumed:
+                    ev.record()
         self.bytes_received = 0
         self.rounds = 0
+
+    @staticmethod
+    def spool_bytes(world: int, max_words_bytes: int, max_sec_bytes: int) -> int:
+        """HBM rank 0 sets aside for the spools."""
+        return 2 * (world - 1) * (max_words_bytes + max_sec_bytes) if world > 1 else 0
+
+    def join(self, stream):
+        """Make `stream` wait for the emitter (rank 0)."""
+        if self.emit_stream is not None:
+            stream.wait_stream(self.emit_stream)
+
+    def _consume_round(self, got, p):
+        import torch
+        if self.consume is None or not got:
+            return
+        if self.emit_stream is None:
+            for src, tw, ts in got:
+                self.consume(src, tw, ts)
+            return
+        cur = torch.cuda.current_stream()
+        self.arrived[p].record(cur)
+        self.emit_stream.wait_event(self.arrived[p])
+        with torch.cuda.stream(self.emit_stream):
+            for src, tw, ts in got:
+                self.consume(src, tw, ts)
+            self.consumed[p].record(self.emit_stream)
 
     def round_fixed(self, mine, peers):
         """Size-exchange-free round: `mine` = (words, sec[:cap], count4) uint8 device tensors of this rank's window or None;
@@ -207,12 +243,17 @@ class GatherRing:
         import torch.distributed as dist
         if self.world == 1:
             return
+        import torch
         ops, got = [], []
+        p = self.rounds & 1
         if self.rank == 0:
+            if self.emit_stream is not None:
+                torch.cuda.current_stream().wait_event(self.consumed[p])      # the emitter is done with this spool set
             for src, (nw, ns) in sorted(peers.items()):
-                if nw > self.spool_w[src].numel() or ns + 4 > self.spool_s[src].numel():
+                sw, ss = self.spool_w[src][p], self.spool_s[src][p]
+                if nw > sw.numel() or ns + 4 > ss.numel():
                     raise RuntimeError(f"gather spool too small for rank {src}: {nw}/{ns} bytes")
-                tw, ts, tc = self.spool_w[src][:nw], self.spool_s[src][:ns], self.spool_s[src][ns:ns + 4]
+                tw, ts, tc = sw[:nw], ss[:ns], ss[ns:ns + 4]
                 ops += [dist.P2POp(dist.irecv, tw, src, group=self.group), dist.P2POp(dist.irecv, ts, src, group=self.group),
                         dist.P2POp(dist.irecv, tc, src, group=self.group)]
                 got.append((src, tw, ts))
@@ -222,9 +263,8 @@ class GatherRing:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        if self.rank == 0 and self.consume is not None:
-            for src, tw, ts in got:
-                self.consume(src, tw, ts)
+        if self.rank == 0:
+            self._consume_round(got, p)
         self.rounds += 1
 
     def round(self, words, sec):
@@ -239,12 +279,16 @@ class GatherRing:
         dist.all_gather_into_tensor(self.all_sizes, self.sizes, group=self.group)
         sz = self.all_sizes.cpu().tolist()
         ops, got = [], []
+        p = self.rounds & 1
         if self.rank == 0:
+            if self.emit_stream is not None:
+                torch.cuda.current_stream().wait_event(self.consumed[p])
             for src in range(1, self.world):
                 nw, ns = int(sz[2 * src]), int(sz[2 * src + 1])
-                if nw > self.spool_w[src].numel() or ns > self.spool_s[src].numel():
+                sw, ss = self.spool_w[src][p], self.spool_s[src][p]
+                if nw > sw.numel() or ns > ss.numel():
                     raise RuntimeError(f"gather spool too small for rank {src}: {nw}/{ns} bytes")
-                tw, ts = self.spool_w[src][:nw], self.spool_s[src][:ns]
+                tw, ts = sw[:nw], ss[:ns]
                 if nw:
                     ops.append(dist.P2POp(dist.irecv, tw, src, group=self.group))
                 if ns:
@@ -259,7 +303,6 @@ class GatherRing:
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        if self.rank == 0 and self.consume is not None:
-            for src, tw, ts in got:
-                self.consume(src, tw, ts)
+        if self.rank == 0:
+            self._consume_round(got, p)
         self.rounds += 1

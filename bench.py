@@ -403,7 +403,7 @@ def run_wgs(args, cfg_name):
     if not resident and not args.no_resident:
         free_b, _ = torch.cuda.mem_get_info(device)
         per_read = synth_cb.DeviceWindow.bytes_per_read()
-        budget = free_b - int(args.hbm_margin_gb * (1 << 30)) - (max_slots * 4 * N_WORDS + (max_slots // 3 + 8192) * SEC_RECORD_BYTES) * (world - 1 if rank == 0 else 0)
+        budget = free_b - int(args.hbm_margin_gb * (1 << 30)) - (st.GatherRing.spool_bytes(world, max_slots * 4 * N_WORDS, (max_slots // 3 + 8192) * SEC_RECORD_BYTES) if rank == 0 else 0)
         shared_scratch = torch.empty(max_reads // synth_cb.BLOCK_READS + 4, dtype=torch.int64, device=device)
         for wi, w in enumerate(my_windows):
             nr = spec.window_reads(w.blk_lo, w.blk_hi)
@@ -468,6 +468,8 @@ def run_wgs(args, cfg_name):
         for r in runners:
             cur.wait_stream(r.stream)
         cur.wait_stream(comm)
+        if ring is not None:
+            ring.join(cur)
 
     def barrier():
         if world > 1:
@@ -519,6 +521,28 @@ def run_wgs(args, cfg_name):
         c1.record()
         barrier()
         nogather_ms = c0.elapsed_time(c1)
+    # link probe (untimed): the same send/recv group with idle SMs — what rank 0's NVLink ingress takes when nothing else runs
+    ingress_gbps = None
+    if world > 1:
+        nprobe = min(w.n_slots for w in all_windows) * 4 * N_WORDS * (len(LIBS) if flags.get("per_lib") else 1)
+        reps = 8
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        src_words = st.alias_device_bytes(runners[0].eng.device_packed().words, nprobe, device) if rank > 0 else None
+        barrier()
+        with torch.cuda.stream(comm):
+            for rep in range(reps + 1):
+                if rep == 1:
+                    p0.record(comm)
+                if rank == 0:
+                    ops = [dist.P2POp(dist.irecv, ring.spool_w[src][0][:nprobe], src) for src in range(1, world)]
+                else:
+                    ops = [dist.P2POp(dist.isend, src_words, 0)]
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            p1.record(comm)
+        torch.cuda.synchronize()
+        barrier()
+        ingress_gbps = nprobe * (world - 1) * reps / (p0.elapsed_time(p1) / 1000.0) / 1e9
     n_my_sites = sum(w.n_sites for w in my_windows)
     per_window_launches = 3 + runners[0].eng.launch_count()     # generator (count, scan, fill) + engine kernels
     launches = len(my_windows) * args.steps * (runners[0].eng.launch_count() if resident else per_window_launches)
@@ -607,7 +631,7 @@ def run_wgs(args, cfg_name):
                 eng2.push_reads(hb)
                 eng2.end_region()
                 eng2._check(eng2.lib.brc_compute(eng2.h))
-                hh += nb
+                hh += eng2.h2d_bytes()          # what crossed PCIe (regular offsets / constant columns are rebuilt on the device)
                 ss += w.n_sites
                 if it == 0:
                     dd += eng2.packed().nbytes()
@@ -663,7 +687,7 @@ def run_wgs(args, cfg_name):
                        "gather": (None if world == 1 else {"transport": "NCCL send/recv of the packed records to rank 0, one group per round",
                                                            "k1_reserved_cta_slots": int(os.environ.get("BRC_K1_RESERVE_CTAS", "0")),
                                                            "rounds_per_step": rounds, "bytes_to_rank0_per_step": ring.bytes_received / max(args.steps + args.warmup, 1),
-                                                           "verified_checksums": gather_ok, "pool_message_records_per_site": args.sec_msg_per_site,
+                                                           "verified_checksums": gather_ok, "rank0_ingress_probe_GBps": ingress_gbps, "pool_message_records_per_site": args.sec_msg_per_site,
                                                            "pool_message_overflows_rank0": gather_overflow,
                                                            "ms_per_step_without_gather": float(t[2]),
                                                            "positions_per_s_without_gather": tot_sites / (float(t[2]) / 1000.0) if float(t[2]) > 0 else None}),

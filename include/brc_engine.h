@@ -303,6 +303,9 @@ BRC_API int brc_fetch_device_results(brc_engine *e, void *stream);
 BRC_API int64_t brc_selftest_fastmath(brc_engine *e, int32_t max_b);
 /* kernels launched by the last brc_run_device/brc_compute (for bench.py's gpu_launches) */
 BRC_API int brc_last_launch_count(const brc_engine *e);
+/* bytes the last brc_compute() of pushed host reads copied host->device (regular offset arrays and constant columns of
+ * fixed-length reads are rebuilt on the device and do not count) */
+BRC_API int64_t brc_last_h2d_bytes(const brc_engine *e);
 /* elapsed GPU milliseconds of the named stage of the last run, measured with CUDA events on the
  * launching stream: 0 = per-read precompute kernel, 1 = pileup kernel, 2 = whole device step */
 BRC_API float brc_last_stage_ms(const brc_engine *e, int stage);
