@@ -26,6 +26,8 @@
 // shortcuts of the hot loop (reciprocal division for small integers, float<->double by bit
 // casts) are exact and checked against the IEEE intrinsics by brc_selftest_fastmath.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cstdlib>
 
 #include "brc_device.cuh"
@@ -40,8 +42,11 @@ __device__ __forceinline__ uint32_t canonical16(uint32_t nib) {
     return (0x5555555455535210ull >> (nib * 4)) & 0xFu;
 }
 
+// one-time, per-device set-up (constant table, opt-in shared-memory sizes, SM count) shared by every engine handle of the
+// process: callers may drive several handles from several host threads, so it is serialised and published with atomics
+static std::mutex g_init_mu;
 static uint8_t h_nt16[256];
-static bool h_nt16_ready = false;
+static bool h_nt16_ready = false;          // guarded by g_init_mu
 static void build_nt16() {
     for (int i = 0; i < 256; ++i) h_nt16[i] = 15;
     const char *s = "=ACMGRSVTWYHKDBN";
@@ -90,13 +95,15 @@ __global__ void ref_encode_kernel(const char *ascii, uint8_t *packed, int64_t n)
 }
 
 static cudaError_t ensure_tables() {
-    if (!h_nt16_ready) build_nt16();
-    static bool uploaded[64] = {false};
+    static std::atomic<bool> uploaded[64];
     int dev = 0; cudaGetDevice(&dev);
-    if (dev < 64 && !uploaded[dev]) {
+    if (dev < 64 && uploaded[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!h_nt16_ready) build_nt16();
+    if (dev >= 64 || !uploaded[dev].load(std::memory_order_relaxed)) {
         cudaError_t e = cudaMemcpyToSymbol(c_nt16, h_nt16, 256);
         if (e != cudaSuccess) return e;
-        uploaded[dev] = true;
+        if (dev < 64) uploaded[dev].store(true, std::memory_order_release);
     }
     return cudaSuccess;
 }
@@ -1043,7 +1050,7 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
     }
 }
 
-static int g_sm_count[64] = {0};
+static std::atomic<int> g_sm_count[64];
 #ifdef BRC_K1_PROFILE
 extern "C" __attribute__((visibility("default"))) void brc_debug_k1prof(unsigned long long *out, int reset) {
     cudaDeviceSynchronize();
@@ -1054,14 +1061,16 @@ extern "C" __attribute__((visibility("default"))) void brc_debug_k1prof(unsigned
 cudaError_t launch_pileup(const PileupParams &p, cudaStream_t s) {
     if (p.tile_count <= 0) return cudaSuccess;
     int dev = 0; cudaGetDevice(&dev);
-    if (dev < 64 && g_sm_count[dev] == 0) {
-        cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    int sms = dev < 64 ? g_sm_count[dev].load(std::memory_order_acquire) : 0;
+    if (sms == 0) {
+        std::lock_guard<std::mutex> lk(g_init_mu);
         cudaError_t e1 = cudaFuncSetAttribute(pileup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PileupSmem));
         cudaError_t e2 = cudaFuncSetAttribute(pileup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PileupSmem));
         if (e1 != cudaSuccess) return e1;
         if (e2 != cudaSuccess) return e2;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+        if (dev < 64) g_sm_count[dev].store(sms, std::memory_order_release);
     }
-    const int sms = dev < 64 && g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
     const int64_t n_work = p.tile_count * (int64_t)p.res.n_rows;
     // persistent CTAs, 3 per SM.  A multi-GPU caller whose NCCL send/recv kernels must run NEXT to this kernel (the ordered-emit
     // gather, bam_readcount_b200/stream.py) leaves a few CTA slots free with BRC_K1_RESERVE_CTAS: a grid that fills every slot
@@ -1449,14 +1458,15 @@ extern "C" __attribute__((visibility("default"))) void brc_debug_deepprof(unsign
 
 cudaError_t launch_deep_sites(const PileupParams &p, cudaStream_t s) {
     if (p.n_deep <= 0 || p.tile_count <= 0) return cudaSuccess;
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64];
     int dev = 0; cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
+    if (dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(g_init_mu);
         cudaError_t e1 = cudaFuncSetAttribute(deep_site_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeepSmem));
         cudaError_t e2 = cudaFuncSetAttribute(deep_site_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeepSmem));
         if (e1 != cudaSuccess) return e1;
         if (e2 != cudaSuccess) return e2;
-        attr_set[dev] = true;
+        if (dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     const dim3 grid((unsigned)p.n_deep, (unsigned)((p.res.n_rows + DEEP_ROWS - 1) / DEEP_ROWS));   // y: batches of DEEP_ROWS libraries
     if (p.per_lib) deep_site_kernel<true><<<grid, DEEP_THREADS, sizeof(DeepSmem), s>>>(p);

@@ -606,9 +606,13 @@ def run_wgs(args, cfg_name):
     # ---- e2e: host buffers through the push path (admission scan + H2D + kernels + D2H of the packed records) ----
     e2e = None
     if args.e2e_windows > 0:
+        import threading
         ne = min(args.e2e_windows, len(my_windows))
-        pool_n = min(2, ne)
-        eng2 = Engine(device=local, **flags)
+        # The caller keeps `nh` engine handles in flight, one host thread each (brc_compute blocks until the window's records are in
+        # host memory): window k+1's upload runs under window k's result download, so both PCIe directions stay busy.
+        nh = max(1, min(args.e2e_handles, ne))
+        pool_n = min(max(2, nh), ne)
+        engs = [Engine(device=local, **flags) for _ in range(nh)]
         hosts = []
         for w in my_windows[:pool_n]:
             hb, _ = spec.window_host(w.contig, w.blk_lo, w.blk_hi)
@@ -616,33 +620,53 @@ def run_wgs(args, cfg_name):
         for c in sorted(set(w.contig for w, _, _ in hosts)):
             lo_p = max(min(w.blk_lo for w, _, _ in hosts if w.contig == c) * synth_cb.BLOCK_BP - 400, 0)
             hi_p = min(spec.contig_len, max(w.end for w, _, _ in hosts if w.contig == c) + 400)
-            eng2.set_reference(c, f"chr{c + 1}", spec.contig_len, spec.ref_host(c, lo_p, hi_p - lo_p), lo_p)
+            for en in engs:
+                en.set_reference(c, f"chr{c + 1}", spec.contig_len, spec.ref_host(c, lo_p, hi_p - lo_p), lo_p)
         h2d = d2h = 0
         sites = 0
         times = []
         for it in range(args.e2e_steps + 1):
+            tally = [[0, 0, 0, None] for _ in range(nh)]
+
+            def handle_loop(i, first_pass=(it == 0)):
+                en, tl = engs[i], tally[i]
+                try:
+                    for k in range(i, ne, nh):
+                        w, hb, nb = hosts[k % pool_n]
+                        en.reset()
+                        en.begin_region(w.contig, w.beg, w.end, False)
+                        en.push_reads(hb)
+                        en.end_region()
+                        en._check(en.lib.brc_compute(en.h))
+                        tl[0] += en.h2d_bytes()      # what crossed PCIe (regular offsets / constant columns are rebuilt on the device)
+                        tl[1] += w.n_sites
+                        if first_pass:
+                            tl[2] += en.packed().nbytes()
+                except Exception as ex:          # surfaced after the join
+                    tl[3] = ex
+
             barrier()
             t0 = time.perf_counter()
-            hh = dd = ss = 0
-            for k in range(ne):
-                w, hb, nb = hosts[k % pool_n]
-                eng2.reset()
-                eng2.begin_region(w.contig, w.beg, w.end, False)
-                eng2.push_reads(hb)
-                eng2.end_region()
-                eng2._check(eng2.lib.brc_compute(eng2.h))
-                hh += eng2.h2d_bytes()          # what crossed PCIe (regular offsets / constant columns are rebuilt on the device)
-                ss += w.n_sites
-                if it == 0:
-                    dd += eng2.packed().nbytes()
+            if nh == 1:
+                handle_loop(0)
+            else:
+                ths = [threading.Thread(target=handle_loop, args=(i,)) for i in range(nh)]
+                for th in ths:
+                    th.start()
+                for th in ths:
+                    th.join()
             dt = time.perf_counter() - t0
+            for tl in tally:
+                if tl[3] is not None:
+                    raise tl[3]
             if it == 0:
-                d2h_per = dd
+                d2h_per = sum(tl[2] for tl in tally)
             else:
                 times.append(dt)
-            h2d, sites = hh, ss
-        eng2.close()
-        e2e = dict(ms=1000.0 * sum(times) / len(times), sites=sites, h2d=h2d, d2h=d2h_per, windows=ne)
+            h2d, sites = sum(tl[0] for tl in tally), sum(tl[1] for tl in tally)
+        for en in engs:
+            en.close()
+        e2e = dict(ms=1000.0 * sum(times) / len(times), sites=sites, h2d=h2d, d2h=d2h_per, windows=ne, handles=nh)
 
     # ---- reduce over ranks: max time, sum of units ----
     t = torch.tensor([elapsed_ms, e2e["ms"] if e2e else 0.0, nogather_ms or 0.0], device=device, dtype=torch.float64)
@@ -702,8 +726,9 @@ def run_wgs(args, cfg_name):
         }
         if e2e:
             line["e2e"] = {"value": float(u[1]) / (e2e_max / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(u[2]), "d2h_bytes_per_step": int(u[3]),
-                           "ms_per_step": e2e_max, "windows_per_rank": e2e["windows"],
-                           "what": "brc_push_reads(pinned host window) + brc_compute per window; results = packed records in pinned host memory"}
+                           "ms_per_step": e2e_max, "windows_per_rank": e2e["windows"], "handles_in_flight": e2e["handles"],
+                           "what": "brc_push_reads(pinned host window) + brc_compute per window, the caller alternating between "
+                                   f"{e2e['handles']} engine handle(s); results = packed records in pinned host memory"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 m = reference_measure(cfg_name, args, 1, 0, size_steps=max(args.steps, 20))
@@ -992,6 +1017,7 @@ def main():
     ap.add_argument("--contigs", type=int, default=0, help="c4: number of contigs (default 24)")
     ap.add_argument("--contig-blocks", type=int, default=0, help="contig length in 1280-bp generator blocks (default per config)")
     ap.add_argument("--e2e-windows", type=int, default=8, help="windows per rank in one e2e step (0 = skip e2e)")
+    ap.add_argument("--e2e-handles", type=int, default=2, help="engine handles (host threads) the e2e caller keeps in flight")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--parity-sites", type=int, default=20_000)
     ap.add_argument("--ref-sample", type=int, default=0, help="sites each reference process handles per step (0 = auto)")
