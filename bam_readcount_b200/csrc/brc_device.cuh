@@ -166,7 +166,11 @@ struct PileupParams {
     const int32_t *deep_tiles;
     int32_t n_deep;
     int32_t deep_min_reads;
+    // tile dispenser of THIS launch (ResultsDev::warn + WARN_WORDS + k, zeroed by init_tiles_kernel); nullptr = fixed stride
+    unsigned long long *work_counter;
 };
+constexpr int WARN_WORDS = 4;          // ResultsDev::warn: [0] SM missing, [1] NM missing, [2..3] spare
+constexpr int N_WORK_COUNTERS = 64;    // followed by one tile dispenser per pileup launch of a run
 
 constexpr int DEEP_MAX_SITES = 2;
 constexpr int DEEP_THREADS = 256;

@@ -423,7 +423,7 @@ static int alloc_outputs(brc_engine *e, int64_t n_reads_cap) {
     if (rs >= 0xFFFFFFFFll) return set_error(e, BRC_E_INVALID, "more than 2^32 (library, site) slots in one batch: window the region");
     CU(e->d_words.reserve(rs1 * 4 * N_WORDS), "cudaMalloc(words)");
     CU(e->d_sec_count.reserve(16), "cudaMalloc(sec_count)");
-    CU(e->d_warn.reserve(32), "cudaMalloc(warn)");
+    CU(e->d_warn.reserve((WARN_WORDS + N_WORK_COUNTERS) * 8), "cudaMalloc(warn)");
     return BRC_OK;
 }
 
@@ -466,6 +466,8 @@ static void make_params(brc_engine *e, const int32_t *d_region_of_read, Precompu
     P1.tiles = e->d_tiles.as<TileInfo>(); P1.tile_lo = P0.tile_lo; P1.tile_hi = P0.tile_hi; P1.n_tiles = (int64_t)e->tiles.size(); P1.tile_begin = 0; P1.tile_count = P1.n_tiles;
     P1.res = results_dev(e);
     P1.deep_tiles = e->deep_tiles.empty() ? nullptr : e->d_deep_tiles.as<int32_t>(); P1.n_deep = (int32_t)e->deep_tiles.size(); P1.deep_min_reads = e->deep_min_reads;
+    static const bool fixed_stride = std::getenv("BRC_K1_STATIC_TILES") != nullptr;      // A/B switch
+    P1.work_counter = fixed_stride ? nullptr : P1.res.warn + WARN_WORDS;                 // launch k of a run takes dispenser k
 }
 
 // K(init) + K0 + K1 on stream s.  Returns BRC_E_OVERFLOW (after syncing) if the secondary pool was too small.
@@ -667,6 +669,7 @@ static int compute_pipelined(brc_engine *e) {
     CU(cudaEventRecord(e->ev[0], sk), "event");
     CU(launch_init_tiles(P0.tile_lo, P0.tile_hi, n_tiles, P1.res.sec_count, P1.res.warn, sk), "launch init_tiles"); e->launch_count++;
     int64_t tile_done = 0;
+    int k1_launches = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t a = n * c / n_chunks, b = n * (c + 1) / n_chunks;
         // ---- kernels: K0 on the chunk, K1 on the tiles it completes ----
@@ -683,6 +686,7 @@ static int compute_pipelined(brc_engine *e) {
         if (tile_to > tile_done) {
             P1.tile_begin = tile_done; P1.tile_count = tile_to - tile_done;
             CU(launch_pileup(P1, sk), "launch pileup"); e->launch_count++;
+            if (P1.work_counter) P1.work_counter = ++k1_launches < N_WORK_COUNTERS ? P1.work_counter + 1 : nullptr;   // next launch: next dispenser
             CU(launch_deep_sites(P1, sk), "launch deep_sites"); if (P1.n_deep) e->launch_count++;
             CU(cudaEventRecord(e->pipe_ev[2 * c + 1], sk), "event");
             if (c < 64) {   // snapshot of the pool counter: the records allocated so far are final (a tile is computed by exactly one launch)

@@ -73,6 +73,7 @@ __global__ void init_tiles_kernel(int32_t *tile_lo, int32_t *tile_hi, int64_t n_
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n_tiles) { tile_lo[i] = 0x7fffffff; tile_hi[i] = 0; }
     if (i == 0) { *sec_count = 0; warn[0] = 0; warn[1] = 0; }
+    if (i < N_WORK_COUNTERS) warn[WARN_WORDS + i] = 0ull;   // tile dispensers of this run's pileup launches
 }
 
 cudaError_t launch_init_tiles(int32_t *tile_lo, int32_t *tile_hi, int64_t n_tiles, int32_t *sec_count,
@@ -936,7 +937,13 @@ __global__ void __launch_bounds__(K1_THREADS, BRC_K1_CTAS_PER_SM) pileup_kernel(
         // =========================== PRODUCER ===========================
         if (lane != 0) return;
         uint32_t item = 0;
-        for (int64_t w = blockIdx.x;; w += gridDim.x) {
+        // Tiles are handed out by an atomic dispenser (zeroed by init_tiles_kernel), not by a fixed stride: SMs that also host
+        // another stream's CTAs (the NCCL send/recv kernels of the ordered-emit gather, a neighbouring window's K0) run their tiles
+        // slower, and with a fixed stride the slowest SM set the launch time (r02m8: 2.8 -> 4.2 ms per window at 4 GPUs).  The
+        // producer runs up to NSTAGE chunks ahead of the consumers, which hides the atomic's round trip.
+        int64_t w_static = blockIdx.x;
+        for (;; w_static += gridDim.x) {
+            const int64_t w = P.work_counter ? (int64_t)atomicAdd(P.work_counter, 1ull) : w_static;
             const bool done = w >= n_work;
             int32_t lo = 0, hi = 0; TileInfo ti{0, 0, 0}; uint32_t row = 0;
             bool narrow = false;
