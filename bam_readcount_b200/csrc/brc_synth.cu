@@ -251,10 +251,33 @@ __global__ void synth_ref_kernel(brc_synth_spec S, int32_t contig, int64_t beg, 
     if (i < len) out[i] = "ACGT"[ref_base(S.seed, (uint64_t)contig, beg + i)];
 }
 
-__global__ void checksum_kernel(const uint32_t *w, int64_t n, unsigned long long *acc) {
+// Checksum of a byte string = sum over its 16-byte groups g of (lo64 ^ rotl(hi64, 29) + 1) * (2 g + 1)  (mod 2^64; a short last
+// group is zero-padded).  One 16-byte load and a handful of integer instructions per group: the emitter stand-in has to read
+// every received byte, not to compete with the pileup kernel for issue slots (the round-2 word-wise mix64 cost rank 0 ~16 % of a
+// pileup launch per round at 4 GPUs).  Position-weighted, so a misplaced or truncated message changes it.
+__device__ __forceinline__ unsigned long long cs_term(unsigned long long lo, unsigned long long hi, int64_t g) {
+    return ((lo ^ ((hi << 29) | (hi >> 35))) + 1ull) * (2ull * (unsigned long long)g + 1ull);
+}
+__global__ void checksum_kernel(const uint32_t *w, int64_t n_words, int aligned16, unsigned long long *acc) {
     unsigned long long s = 0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        s += mix64(((uint64_t)w[i] << 32) ^ (uint64_t)i);
+    const int64_t n_groups = (n_words + 3) / 4, n_full = n_words / 4;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    if (aligned16) {
+        const uint4 *v = reinterpret_cast<const uint4 *>(w);
+        for (int64_t g = t0; g < n_full; g += step) {
+            const uint4 x = v[g];
+            s += cs_term((unsigned long long)x.x | ((unsigned long long)x.y << 32), (unsigned long long)x.z | ((unsigned long long)x.w << 32), g);
+        }
+    } else {
+        for (int64_t g = t0; g < n_full; g += step)
+            s += cs_term((unsigned long long)w[4 * g] | ((unsigned long long)w[4 * g + 1] << 32),
+                         (unsigned long long)w[4 * g + 2] | ((unsigned long long)w[4 * g + 3] << 32), g);
+    }
+    if (t0 == 0 && n_groups > n_full) {          // zero-padded last group
+        uint32_t x[4] = {0u, 0u, 0u, 0u};
+        for (int64_t k = 4 * n_full; k < n_words; ++k) x[k - 4 * n_full] = w[k];
+        s += cs_term((unsigned long long)x[0] | ((unsigned long long)x[1] << 32), (unsigned long long)x[2] | ((unsigned long long)x[3] << 32), n_full);
+    }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     __shared__ unsigned long long red[32];
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -430,8 +453,8 @@ int brc_synth_checksum_device(const void *buf_dev, int64_t n_bytes, unsigned lon
     if (!buf_dev || !acc_dev || n_bytes < 0 || (n_bytes & 3)) return BRC_E_INVALID;
     if (n_bytes == 0) return BRC_OK;
     const int64_t n = n_bytes / 4;
-    const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, (n + 255) / 256);
-    checksum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(buf_dev), n, acc_dev);
+    const unsigned grid = (unsigned)std::min<int64_t>(148 * 2, (n / 4 + 255) / 256 + 1);       // 2 CTAs per SM: a reader, not a tenant
+    checksum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(buf_dev), n, ((uintptr_t)buf_dev & 15) == 0 ? 1 : 0, acc_dev);
     return cudaGetLastError() == cudaSuccess ? BRC_OK : BRC_E_CUDA;
 }
 

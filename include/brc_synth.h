@@ -86,8 +86,9 @@ BRC_API int brc_synth_fill_device(const brc_synth_spec *spec, int32_t contig, in
 BRC_API int brc_synth_write_sam(const brc_synth_spec *spec, int32_t contig, int64_t blk_lo, int64_t blk_hi, const char *path,
                                 const char *contig_name, int64_t declared_len, int n_threads);
 
-/* 64-bit checksum of a device buffer (order-independent sum of mixed 32-bit words + positions): the stand-in for the
- * ordered emit's consumer in bench.py and the integrity check of the NCCL gather.  Adds into *acc_dev (device u64). */
+/* 64-bit checksum of a device buffer: sum over its 16-byte groups g of ((lo64 ^ rotl(hi64, 29)) + 1) * (2 g + 1), the last group
+ * zero-padded (n_bytes must be a multiple of 4).  One 16-byte load per group: the stand-in for the ordered emit's consumer in
+ * bench.py (it reads every received byte) and the integrity check of the NCCL gather.  Adds into *acc_dev (device u64). */
 BRC_API int brc_synth_checksum_device(const void *buf_dev, int64_t n_bytes, unsigned long long *acc_dev, void *stream);
 
 #ifdef __cplusplus

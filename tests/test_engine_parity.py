@@ -4,6 +4,7 @@
       bit-exact (integers AND the float32 sums: accumulation order is preserved);
   (3) the reference's warning counters.
 """
+import numpy as np
 import pytest
 
 import cases
@@ -273,3 +274,72 @@ def test_carried_deletion_queue_equals_one_batch():
         finally:
             e.close()
         assert one == cases.load_golden_text(f"edge_alleles_{fl_name}.txt")
+
+
+def test_two_handles_driven_from_two_threads():
+    """bench.py's e2e caller keeps two engine handles in flight, one host thread each (brc_compute blocks): both must give what a
+    lone handle gives — the per-device set-up they share (constant table, opt-in shared-memory sizes) is serialised."""
+    import threading
+    from bam_readcount_b200.engine import Engine
+    jobs = []
+    for seed, L in ((21, 9000), (22, 7000)):
+        jobs.append((cases.synthetic_case(L=L, depth=30, seed=seed, regions=((0, 1, L),)), dict(min_mapq=20, min_bq=20), L))
+
+    def run(i, reps, out):
+        case, flags, L = jobs[i]
+        name, clen, seq, wb = case["contigs"][0]
+        eng = Engine(**flags)
+        try:
+            for rep in range(reps):                    # reuse of a handle while the other one is mid-compute
+                eng.reset()
+                eng.set_reference(0, name, clen, seq, wb)
+                eng.begin_region(0, 0, L, False)
+                eng.push_reads(case["batch"])
+                eng.end_region()
+                eng.compute()
+                out.append(eng.format_text())
+        finally:
+            eng.close()
+
+    alone = [[], []]
+    for i in range(2):
+        run(i, 1, alone[i])
+    outs = [[], []]
+    ths = [threading.Thread(target=run, args=(i, 3, outs[i])) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    for i in range(2):
+        assert len(outs[i]) == 3 and len(alone[i][0]) > 100000
+        for rep in range(3):
+            assert outs[i][rep] == alone[i][0], (i, rep, _first_diff(outs[i][rep], alone[i][0]))
+
+
+def test_h2d_byte_report_counts_what_crossed_pcie(monkeypatch):
+    """brc_last_h2d_bytes: regular offset arrays and constant columns of fixed-length reads are rebuilt on the device and are not
+    counted; with the elision off every array of the batch is."""
+    from bam_readcount_b200.engine import Engine
+    case = cases.synthetic_case(L=8000, depth=30, seed=5, regions=((0, 1, 8000),))
+    name, clen, seq, wb = case["contigs"][0]
+    b = case["batch"]
+    n = b.n_reads
+    full = sum(int(np.asarray(a).nbytes) for a in (b.pos, b.flag, b.mapq, b.lib, b.l_qseq, b.nm, b.sm, b.cigar_off, b.cigar, b.seq_off, b.seq,
+                                                    b.qual_off, b.qual) if a is not None)
+    got = {}
+    for mode in ("elide", "all"):
+        if mode == "all":
+            monkeypatch.setenv("BRC_NO_H2D_ELISION", "1")
+        eng = Engine(min_mapq=20)
+        try:
+            eng.set_reference(0, name, clen, seq, wb)
+            eng.begin_region(0, 0, 8000, False)
+            eng.push_reads(b)
+            eng.end_region()
+            eng.compute()
+            got[mode] = (eng.h2d_bytes(), eng.format_text())
+        finally:
+            eng.close()
+    assert got["elide"][1] == got["all"][1]
+    assert 0 < got["elide"][0] <= got["all"][0] <= full + 4 * n + 64
+    assert got["all"][0] >= full - 16 * n - 64          # never less than the arrays that cannot be rebuilt

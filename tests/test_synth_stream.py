@@ -300,3 +300,41 @@ def test_site_at_50000x_eight_libraries_is_bit_exact():
             assert int(res.ncover[:, 1].sum()) == 50_000
         finally:
             e.close()
+
+
+@pytest.mark.gpu
+def test_gather_checksum_is_a_function_of_the_bytes_only():
+    """bench.py verifies the NCCL gather by comparing the senders' checksums with rank 0's: the value must not depend on the
+    buffer's alignment, must match the documented formula (include/brc_synth.h) and must move when a byte or a length does."""
+    import torch
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+
+    def formula(b: bytes) -> int:
+        w = np.frombuffer(b + b"\0" * (-len(b) % 16), dtype="<u8").reshape(-1, 2)
+        lo, hi = w[:, 0], w[:, 1]
+        rot = (hi << np.uint64(29)) | (hi >> np.uint64(35))
+        g = np.arange(len(w), dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            return int((((lo ^ rot) + np.uint64(1)) * (np.uint64(2) * g + np.uint64(1))).sum(dtype=np.uint64))
+
+    def device(t) -> int:
+        acc = torch.zeros(1, dtype=torch.int64, device=dev)
+        synth_cb.checksum_device(t, acc, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return int(acc.cpu().numpy().view(np.uint64)[0])
+
+    for n in (4, 12, 16, 20, 4096, 1_000_004, 3_000_000):
+        raw = rng.integers(0, 256, n, dtype=np.uint8)
+        want = formula(raw.tobytes())
+        base = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+        for off in (0, 4, 8, 16):                                   # 16-byte aligned and not
+            view = base[off:off + n]
+            view.copy_(torch.from_numpy(raw))
+            assert device(view) == want, (n, off)
+        flipped = raw.copy(); flipped[n // 2] ^= 1
+        view.copy_(torch.from_numpy(flipped))
+        assert device(view) != want
+        if n > 4:
+            view.copy_(torch.from_numpy(raw))
+            assert device(view[:n - 4]) != want
