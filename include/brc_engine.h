@@ -28,7 +28,10 @@
  *
  * Plain pointers and sizes only; no C++ or torch types cross this boundary; nothing throws.
  * All functions return 0 (BRC_OK) or a negative brc_status.  One caller thread per handle
- * (the reference's callbacks are not re-entrant either, SURVEY.md §8b "Threading").
+ * (the reference's callbacks are not re-entrant either, SURVEY.md §8b "Threading"); different
+ * handles are independent and may be driven from different threads at the same time (their
+ * streams, device buffers and pinned host buffers are their own; the process-wide per-device
+ * set-up is serialised inside the library).
  * The library REQUIRES a CUDA device: there is no CPU fallback (brc_create fails with
  * BRC_E_NO_DEVICE when none is usable).
  */
