@@ -320,7 +320,7 @@ def test_gather_checksum_is_a_function_of_the_bytes_only():
 
     def device(t) -> int:
         acc = torch.zeros(1, dtype=torch.int64, device=dev)
-        synth_cb.checksum_device(t, acc, torch.cuda.current_stream().cuda_stream)
+        sc.checksum_device(t, acc, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         return int(acc.cpu().numpy().view(np.uint64)[0])
 
