@@ -24,7 +24,10 @@
 #include <vector>
 #include <zlib.h>
 #include <chrono>
+#include <future>
+#include <memory>
 #include <thread>
+#include <unordered_map>
 #include <unistd.h>
 
 #include "../../include/brc_engine.h"
@@ -60,6 +63,8 @@ struct Bgzf {
         n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
         return fp != nullptr;
     }
+    // a reader owned by ONE decode thread of ParallelFetcher: inflates inline, short read-ahead spans
+    bool open_worker(const std::string &path) { fp = std::fopen(path.c_str(), "rb"); n_threads = 1; span_blocks = 16; return fp != nullptr; }
     ~Bgzf() { if (fp) std::fclose(fp); }
 
     static bool inflate_block(const uint8_t *src, size_t clen, std::vector<uint8_t> &dst, uint32_t isize) {
@@ -467,6 +472,12 @@ struct Warner {
         c.qname = (const char *)(r.data.data() + 32);
         cands.push_back(std::move(c)); regs.back().c1 = cands.size();
     }
+    // candidates collected by a parallel decode (ParallelFetcher), already in file order
+    void take(std::vector<Cand> &more) {
+        if (!collecting() || regs.empty()) { more.clear(); return; }
+        for (Cand &c : more) cands.push_back(std::move(c));
+        more.clear(); regs.back().c1 = cands.size();
+    }
     void emit(int type, const std::string &qname) {
         static const char *msg[NT] = {"Couldn't find single-end mapping quality. Check to see if the SM tag is in BAM.",
                                       "Couldn't find number of mismatches. Check to see if the NM tag is in BAM.",
@@ -527,6 +538,169 @@ struct Warner {
         if (!unlimited) return;
         static const char *nm[NT] = {"SM tag missing", "NM tag missing", "generated tag missing", "library unavailable"};
         for (int t = 0; t < NT; ++t) if (engine_counts[t] > max_per_type) std::fprintf(stderr, "WARNING: %s: %lld events in total (only the first %lld are listed)\n", nm[t], (long long)engine_counts[t], max_per_type);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// Parallel decode of one big fetch (a window of a cut region): the position range is cut at 16 kb linear-index boundaries
+// into one sub-range per thread; every thread has its own BGZF reader, seeks through the index and keeps the records whose
+// START lies in its sub-range (the first thread also keeps the earlier records that reach into the fetch), so the slices
+// concatenated in thread order are exactly samfetch's records in file order.  Each slice is decoded straight into the
+// struct-of-arrays layout of brc_read_batch; the slices are then copied (in parallel) into ONE page-locked batch that
+// brc_push_reads borrows, so the engine's pipelined upload runs out of it with no further host copy.
+// Unmapped records are dropped here (the pileup buffer refuses them, V:htslib-1.10/sam.c:4488-4490).
+// ------------------------------------------------------------------------------------------
+struct Slice {
+    std::vector<int32_t> pos, l_qseq, nm, sm; std::vector<uint16_t> flag, lib; std::vector<uint8_t> mapq;
+    std::vector<uint64_t> cigar_off, seq_off, qual_off; std::vector<uint32_t> cigar; std::vector<uint8_t> seq, qual;
+    std::vector<Warner::Cand> cands; bool cand_overflow = false, error = false; uint64_t n_decoded = 0;
+    void clear() {
+        pos.clear(); l_qseq.clear(); nm.clear(); sm.clear(); flag.clear(); lib.clear(); mapq.clear();
+        cigar_off.assign(1, 0); seq_off.assign(1, 0); qual_off.assign(1, 0); cigar.clear(); seq.clear(); qual.clear();
+        cands.clear(); cand_overflow = false; error = false; n_decoded = 0;
+    }
+    size_t n() const { return pos.size(); }
+};
+
+struct PinnedBuf {   // grow-only host buffer: page-locked through the engine when there is one (brc_host_alloc), plain otherwise
+    void *p = nullptr; size_t cap = 0; bool pinned = false;
+    bool reserve(size_t bytes, bool want_pinned) {
+        if (bytes <= cap) return true;
+        release();
+        const size_t want = bytes + bytes / 8 + 4096;
+        if (want_pinned && brc_host_alloc(want, &p) == BRC_OK && p) { pinned = true; cap = want; return true; }
+        p = std::malloc(want); pinned = false; cap = p ? want : 0;
+        return p != nullptr;
+    }
+    void release() { if (p) { if (pinned) brc_host_free(p); else std::free(p); } p = nullptr; cap = 0; }
+    ~PinnedBuf() { release(); }
+    PinnedBuf() = default; PinnedBuf(const PinnedBuf &) = delete; PinnedBuf &operator=(const PinnedBuf &) = delete;
+};
+
+struct WindowJob {   // one decoded window: the slices and the concatenated batch
+    std::vector<Slice> slices;
+    PinnedBuf buf[13];
+    brc_read_batch batch{};
+    uint64_t n_decoded = 0; bool error = false, cand_overflow = false;
+    int tid = -1; int64_t fbeg = 0, fend = 0;
+};
+
+struct ParallelFetcher {
+    const BamFile &bam; std::string path; int n_threads; bool per_lib, want_pinned;
+    std::unordered_map<std::string, uint16_t> rg_lib;      // @RG ID -> library rank
+    std::vector<std::unique_ptr<Bgzf>> readers;
+    static constexpr size_t MAX_CANDS = 65536;
+
+    ParallelFetcher(const BamFile &b, const std::string &p, bool pl, bool pin) : bam(b), path(p), per_lib(pl), want_pinned(pin) {
+        unsigned hw = std::thread::hardware_concurrency();
+        n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+        if (const char *ov = std::getenv("BRC_CLI_DECODE_THREADS")) n_threads = std::max(1, std::atoi(ov));
+    }
+    static bool eligible(int64_t fbeg, int64_t fend) { return fend - fbeg >= (int64_t(1) << 18); }   // >= 16 linear-index windows
+
+    // records of contig `tid` with lo <= pos < hi (first slice: also pos < lo with endpos > fbeg), in file order
+    void decode_slice(Bgzf &bz, int tid, int64_t lo, int64_t hi, bool first, int64_t fbeg, bool collect, Slice &out) const {
+        out.clear();
+        uint64_t voff;
+        if (!bam.query_offset(tid, lo, voff)) return;
+        if (!bz.seek(voff)) { out.error = bz.error; return; }
+        Rec r;
+        for (;;) {
+            if (!read_record(bz, r)) { out.error = bz.error; break; }
+            if (r.tid != tid || r.pos >= hi) break;
+            ++out.n_decoded;
+            if (r.pos < lo) {
+                if (!first) continue;
+                r.endpos = rec_endpos(r);
+                if (r.endpos <= fbeg) continue;
+            }
+            if (r.flag & 4) continue;
+            uint16_t lib = 0; bool no_lib = false;
+            if (per_lib) {
+                lib = (uint16_t)BRC_LIB_NONE;
+                if (r.has_rg) { auto it = rg_lib.find(r.rg); if (it != rg_lib.end()) lib = it->second; }
+                no_lib = lib == (uint16_t)BRC_LIB_NONE;
+            }
+            if (collect && !out.cand_overflow) {
+                const bool no_nm = r.nm == BRC_TAG_ABSENT, no_sm = (r.flag & 2) && r.sm == BRC_TAG_ABSENT;
+                if (no_nm || no_sm || no_lib) {
+                    if (out.cands.size() >= MAX_CANDS) out.cand_overflow = true;
+                    else {
+                        Warner::Cand c; c.pos = r.pos; c.endpos = rec_endpos(r); c.flag = r.flag; c.mapq = r.mapq; c.no_nm = no_nm; c.no_sm = no_sm; c.no_lib = no_lib;
+                        c.cigar.assign(r.cigar, r.cigar + r.n_cigar); c.qual.assign(r.qual, r.qual + r.l_qseq); c.qname = (const char *)(r.data.data() + 32);
+                        out.cands.push_back(std::move(c));
+                    }
+                }
+            }
+            out.pos.push_back(r.pos); out.flag.push_back(r.flag); out.mapq.push_back(r.mapq); out.lib.push_back(lib); out.l_qseq.push_back(r.l_qseq);
+            out.nm.push_back(r.nm); out.sm.push_back(r.sm);
+            out.cigar.insert(out.cigar.end(), r.cigar, r.cigar + r.n_cigar); out.cigar_off.push_back(out.cigar.size());
+            out.seq.insert(out.seq.end(), r.seq, r.seq + ((size_t)r.l_qseq + 1) / 2); out.seq_off.push_back(out.seq.size());
+            out.qual.insert(out.qual.end(), r.qual, r.qual + r.l_qseq); out.qual_off.push_back(out.qual.size());
+        }
+    }
+
+    // decode [fbeg, fend) of `tid` into job.slices and job.batch; false when a reader could not be opened
+    bool run(int tid, int64_t fbeg, int64_t fend, bool collect, WindowJob &job) {
+        job.tid = tid; job.fbeg = fbeg; job.fend = fend; job.error = false; job.cand_overflow = false; job.n_decoded = 0;
+        const int64_t w0 = fbeg >> 14, w1 = (fend + 16383) >> 14;
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (w1 - w0) / 4));
+        while ((int)readers.size() < T) { readers.emplace_back(new Bgzf()); if (!readers.back()->open_worker(path)) return false; }
+        job.slices.resize((size_t)T);
+        std::vector<int64_t> cut((size_t)T + 1);
+        for (int t = 0; t <= T; ++t) cut[(size_t)t] = t == 0 ? fbeg : t == T ? fend : ((w0 + (w1 - w0) * t / T) << 14);
+        auto work = [&](int t) { decode_slice(*readers[(size_t)t], tid, cut[(size_t)t], cut[(size_t)t + 1], t == 0, fbeg, collect, job.slices[(size_t)t]); };
+        const bool timing = std::getenv("BRC_CLI_TIMING") != nullptr;
+        auto clk = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = clk();
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+        }
+        const double t1 = clk();
+        // ---- concatenate: prefix sums, then every thread copies its slice ----
+        std::vector<size_t> rn((size_t)T + 1, 0), cn((size_t)T + 1, 0), sn((size_t)T + 1, 0), qn((size_t)T + 1, 0);
+        for (int t = 0; t < T; ++t) {
+            const Slice &sl = job.slices[(size_t)t];
+            rn[(size_t)t + 1] = rn[(size_t)t] + sl.n(); cn[(size_t)t + 1] = cn[(size_t)t] + sl.cigar.size();
+            sn[(size_t)t + 1] = sn[(size_t)t] + sl.seq.size(); qn[(size_t)t + 1] = qn[(size_t)t] + sl.qual.size();
+            job.error = job.error || sl.error; job.cand_overflow = job.cand_overflow || sl.cand_overflow; job.n_decoded += sl.n_decoded;
+        }
+        const size_t n = rn[(size_t)T];
+        const size_t bytes[13] = {n * 4, n * 2, n, n * 2, n * 4, n * 4, n * 4, (n + 1) * 8, cn[(size_t)T] * 4, (n + 1) * 8, sn[(size_t)T], (n + 1) * 8, qn[(size_t)T]};
+        for (int k = 0; k < 13; ++k) if (!job.buf[k].reserve(bytes[k] + 64, want_pinned)) return false;
+        int32_t *pos = (int32_t *)job.buf[0].p; uint16_t *flag = (uint16_t *)job.buf[1].p; uint8_t *mapq = (uint8_t *)job.buf[2].p; uint16_t *lib = (uint16_t *)job.buf[3].p;
+        int32_t *lq = (int32_t *)job.buf[4].p, *nm = (int32_t *)job.buf[5].p, *sm = (int32_t *)job.buf[6].p;
+        uint64_t *coff = (uint64_t *)job.buf[7].p; uint32_t *cig = (uint32_t *)job.buf[8].p; uint64_t *soff = (uint64_t *)job.buf[9].p; uint8_t *seq = (uint8_t *)job.buf[10].p;
+        uint64_t *qoff = (uint64_t *)job.buf[11].p; uint8_t *qual = (uint8_t *)job.buf[12].p;
+        auto copy = [&](int t) {
+            const Slice &sl = job.slices[(size_t)t];
+            const size_t r0 = rn[(size_t)t], m = sl.n();
+            if (m) {
+                std::memcpy(pos + r0, sl.pos.data(), m * 4); std::memcpy(flag + r0, sl.flag.data(), m * 2); std::memcpy(mapq + r0, sl.mapq.data(), m);
+                std::memcpy(lib + r0, sl.lib.data(), m * 2); std::memcpy(lq + r0, sl.l_qseq.data(), m * 4); std::memcpy(nm + r0, sl.nm.data(), m * 4);
+                std::memcpy(sm + r0, sl.sm.data(), m * 4);
+                if (!sl.cigar.empty()) std::memcpy(cig + cn[(size_t)t], sl.cigar.data(), sl.cigar.size() * 4);
+                if (!sl.seq.empty()) std::memcpy(seq + sn[(size_t)t], sl.seq.data(), sl.seq.size());
+                if (!sl.qual.empty()) std::memcpy(qual + qn[(size_t)t], sl.qual.data(), sl.qual.size());
+                for (size_t i = 0; i < m; ++i) { coff[r0 + i] = cn[(size_t)t] + sl.cigar_off[i]; soff[r0 + i] = sn[(size_t)t] + sl.seq_off[i]; qoff[r0 + i] = qn[(size_t)t] + sl.qual_off[i]; }
+            }
+            if (t == T - 1) { coff[n] = cn[(size_t)T]; soff[n] = sn[(size_t)T]; qoff[n] = qn[(size_t)T]; }
+        };
+        {
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(copy, t);
+            copy(0);
+            for (auto &x : th) x.join();
+        }
+        if (timing) std::fprintf(stderr, "[brc timing] window %d:%lld-%lld: %d threads decode %.3fs, concatenate %.3fs (%zu reads)\n", tid, (long long)fbeg, (long long)fend, T, t1 - t0, clk() - t1, n);
+        brc_read_batch &b = job.batch;
+        b = brc_read_batch{};
+        b.n_reads = (int64_t)n; b.tid = nullptr; b.pos = pos; b.flag = flag; b.mapq = mapq; b.lib = lib; b.l_qseq = lq; b.nm = nm; b.sm = sm;
+        b.cigar_off = coff; b.cigar = cig; b.seq_off = soff; b.seq = seq; b.qual_off = qoff; b.qual = qual;
+        return true;
     }
 };
 
@@ -810,6 +984,43 @@ int main(int argc, char **argv) {
     if (eng) brc_set_queue_carry(eng, 1);    // argv regions are flushed batch by batch: their never-cleared deletion queue travels with the engine
     const double t_loop0 = now();
     RegionFetcher fetcher(bam);
+    // big fetches (windows of a cut region) are decoded by several threads, one window ahead of the engine (ParallelFetcher)
+    ParallelFetcher pf(bam, bam_path, per_lib, eng != nullptr);
+    for (const auto &kv : rg_lb) pf.rg_lib[kv.first] = lib_rank[kv.second];
+    const bool allow_parallel = !is_cram && !device_decode && std::getenv("BRC_CLI_SEQUENTIAL") == nullptr;
+    std::unique_ptr<WindowJob[]> jobs(new WindowJob[2]);
+    std::future<bool> ahead; size_t ahead_gi = (size_t)-1; int ahead_slot = 0;
+    bool par_decode_error = false; uint64_t par_decoded = 0, par_windows = 0;
+    auto fetch_range = [&](size_t gi, int64_t &fb, int64_t &fe) {
+        const Region &g = regions[gi];
+        const int64_t clen = bam.lens[(size_t)g.tid];
+        fb = std::max<int64_t>((int64_t)g.beg - 1, 0);
+        fe = std::min<int64_t>(g.end, std::max<int64_t>(clen, (int64_t)g.beg + 1));
+    };
+    auto par_ok = [&](size_t gi) {
+        if (!allow_parallel || gi >= regions.size()) return false;
+        int64_t fb, fe; fetch_range(gi, fb, fe);
+        return ParallelFetcher::eligible(fb, fe);
+    };
+    auto start_decode = [&](size_t gi, int slot) {
+        int64_t fb, fe; fetch_range(gi, fb, fe);
+        const int tid = regions[gi].tid; const bool collect = warner.collecting();
+        WindowJob *job = &jobs[slot]; ParallelFetcher *pfp = &pf;
+        return std::async(std::launch::async, [pfp, job, tid, fb, fe, collect] { return pfp->run(tid, fb, fe, collect, *job); });
+    };
+    // the decoded window for region gi (prefetched or decoded now); nullptr = take the sequential path
+    auto decoded_window = [&](size_t gi) -> WindowJob * {
+        int slot = 0; bool ok;
+        if (ahead.valid() && ahead_gi == gi) { ok = ahead.get(); slot = ahead_slot; }
+        else { if (ahead.valid()) ahead.get(); ok = start_decode(gi, 0).get(); }
+        ahead_gi = (size_t)-1;
+        WindowJob *job = &jobs[slot];
+        if (ok && gi + 1 < regions.size() && par_ok(gi + 1)) { ahead_slot = slot ^ 1; ahead_gi = gi + 1; ahead = start_decode(gi + 1, ahead_slot); }
+        if (!ok) return nullptr;
+        if (job->cand_overflow && warner.collecting()) return nullptr;      // a BAM full of untagged reads: the per-read warning replay wants them all
+        par_decode_error = par_decode_error || job->error; par_decoded += job->n_decoded; ++par_windows;
+        return job;
+    };
     auto next_fbeg = [&](size_t gi) -> int64_t {   // start of the following fetch when it continues this one, else "keep nothing"
         if (gi + 1 >= regions.size() || regions[gi + 1].tid != regions[gi].tid) return INT64_MAX;
         return std::max<int64_t>((int64_t)regions[gi + 1].beg - 1, 0);
@@ -820,7 +1031,15 @@ int main(int argc, char **argv) {
         if (decode_only) {
             const int64_t fbeg = std::max<int64_t>((int64_t)g.beg - 1, 0), fend = g.end;
             int64_t n = 0, psum = 0, qsum = 0;
-            auto count = [&](const Rec &r) { ++n; psum += r.pos; for (int k = 0; k < r.l_qseq; ++k) qsum += r.qual[k]; };
+            auto count = [&](const Rec &r) { if (r.flag & 4) return; ++n; psum += r.pos; for (int k = 0; k < r.l_qseq; ++k) qsum += r.qual[k]; };
+            WindowJob *job = par_ok(gi) ? decoded_window(gi) : nullptr;
+            if (job) {
+                const brc_read_batch &b = job->batch;
+                n = b.n_reads;
+                for (int64_t i = 0; i < b.n_reads; ++i) psum += b.pos[i];
+                for (uint64_t k = b.qual_off[0]; k < b.qual_off[b.n_reads]; ++k) qsum += b.qual[k];
+                fetcher.active = false;
+            } else
 #ifdef BRC_WITH_HTSLIB
             if (is_cram) hts.fetch(g.tid, fbeg, fend, count); else
 #endif
@@ -836,6 +1055,26 @@ int main(int argc, char **argv) {
             t_ref += now() - d0;
         }
         const double d1 = now();
+        if (par_ok(gi)) {
+            // one window = one batch: whatever smaller regions are pending goes out first, then the window is pushed as ONE borrowed
+            // batch (the engine streams it to the GPU in chunks) while the next window is already being decoded
+            if (pushed > 0) { if (flush() != BRC_OK) { brc_destroy(eng); return 1; } pushed = 0; }
+            if (WindowJob *job = decoded_window(gi)) {
+                brc_begin_region(eng, g.tid, g.beg, g.end, g.site_list ? 1 : 0);
+                warner.begin_region(g.tid, g.beg, g.end, g.cont);
+                for (Slice &sl : job->slices) warner.take(sl.cands);
+                if (job->batch.n_reads > 0) {
+                    const int prc = brc_push_reads(eng, &job->batch);
+                    if (prc != BRC_OK) { std::fprintf(stderr, "brc_push_reads: %s\n", brc_last_error(eng)); brc_destroy(eng); return 1; }
+                }
+                brc_end_region(eng);
+                fetcher.active = false;
+                t_decode += now() - d1;
+                if (flush() != BRC_OK) { brc_destroy(eng); return 1; }     // the batch is borrowed until the text is out
+                pushed = 0;
+                continue;
+            }
+        }
         brc_begin_region(eng, g.tid, g.beg, g.end, g.site_list ? 1 : 0);
         warner.begin_region(g.tid, g.beg, g.end, g.cont);
         // samfetch(in, idx, ref, d.beg-1, d.end): records with tid, endpos > max(beg-1,0), pos < end, in file order
@@ -880,12 +1119,14 @@ int main(int argc, char **argv) {
     }
     warner.finish(warn_total);
 #ifdef BRC_WITH_HTSLIB
-    const bool decode_error = bam.bz.error || hts.error;
+    const bool decode_error = bam.bz.error || hts.error || par_decode_error;
 #else
-    const bool decode_error = bam.bz.error;
+    const bool decode_error = bam.bz.error || par_decode_error;
 #endif
+    if (ahead.valid()) ahead.get();
     if (decode_error) std::fprintf(stderr, "[E::bgzf_read] %s: truncated or corrupt BGZF block / BAM record — the output above is incomplete\n", bam_path.c_str());
-    if (timing) std::fprintf(stderr, "[brc timing] index seeks %llu  records decoded %llu\n", (unsigned long long)fetcher.n_seeks, (unsigned long long)fetcher.n_decoded);
+    if (timing) std::fprintf(stderr, "[brc timing] index seeks %llu  records decoded %llu  (+ %llu records in %llu windows decoded by %d threads)\n", (unsigned long long)fetcher.n_seeks,
+                             (unsigned long long)fetcher.n_decoded, (unsigned long long)par_decoded, (unsigned long long)par_windows, pf.n_threads);
     if (decode_only) return decode_error ? 1 : 0;
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
     const double t_d0 = now();

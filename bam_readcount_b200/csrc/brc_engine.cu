@@ -6,6 +6,7 @@
 // host, in file order), end_region ≙ bam_plbuf_push(0).  All arithmetic of the hot path runs
 // in the CUDA kernels of brc_kernels.cu; this file only batches, copies and launches.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,8 @@ const char *brc_strerror(int s) {
 
 const char *brc_last_error(const brc_engine *e) { return e ? e->err.c_str() : ""; }
 
+static std::atomic<int> g_last_device{-1};      // device of the most recent brc_create: where brc_host_alloc page-locks
+
 int brc_create(const brc_config *cfg, brc_engine **out) {
     if (!cfg || !out) return BRC_E_INVALID;
     *out = nullptr;
@@ -62,6 +65,7 @@ int brc_create(const brc_config *cfg, brc_engine **out) {
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) { cudaGetLastError(); return BRC_E_NO_DEVICE; }
     if (cfg->device < 0 || cfg->device >= n_dev) return BRC_E_NO_DEVICE;
     if (cudaSetDevice(cfg->device) != cudaSuccess) { cudaGetLastError(); return BRC_E_NO_DEVICE; }
+    g_last_device.store(cfg->device, std::memory_order_relaxed);
     brc_engine *e = new (std::nothrow) brc_engine();
     if (!e) return BRC_E_NOMEM;
     e->cfg = *cfg;
@@ -955,6 +959,17 @@ int64_t brc_selftest_fastmath(brc_engine *e, int32_t max_b) {
     if (ce != cudaSuccess) return set_cuda_error(e, ce, "fastmath selftest");
     return (int64_t)h_bad;
 }
+int brc_host_alloc(size_t bytes, void **out) {
+    if (!out) return BRC_E_INVALID;
+    *out = nullptr;
+    const int dev = g_last_device.load(std::memory_order_relaxed);          // a caller thread that never touched CUDA sits on device 0
+    if (dev >= 0 && cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return BRC_E_NO_DEVICE; }
+    if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return BRC_E_NO_DEVICE; }
+    return BRC_OK;
+}
+
+void brc_host_free(void *p) { if (p) { cudaFreeHost(p); cudaGetLastError(); } }
+
 int64_t brc_last_h2d_bytes(const brc_engine *e) { return e ? e->h2d_bytes_last : 0; }
 
 float brc_last_stage_ms(const brc_engine *e, int stage) {

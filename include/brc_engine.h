@@ -305,6 +305,12 @@ BRC_API int brc_fetch_device_results(brc_engine *e, void *stream);
  * against the IEEE intrinsics for every divisor 1..max_b; returns the number of mismatches (0 = ok). */
 BRC_API int64_t brc_selftest_fastmath(brc_engine *e, int32_t max_b);
 /* kernels launched by the last brc_run_device/brc_compute (for bench.py's gpu_launches) */
+/* Page-locked host memory for batches handed to brc_push_reads (a borrowed batch is DMA'd straight out of the caller's arrays:
+ * from pageable memory the copies are staged and synchronous).  cudaHostAlloc / cudaFreeHost behind plain pointers, so that a host
+ * written against this header does not need the CUDA runtime.  BRC_E_NO_DEVICE without a usable device. */
+BRC_API int brc_host_alloc(size_t bytes, void **out);
+BRC_API void brc_host_free(void *p);
+
 BRC_API int brc_last_launch_count(const brc_engine *e);
 /* bytes the last brc_compute() of pushed host reads copied host->device (regular offset arrays and constant columns of
  * fixed-length reads are rebuilt on the device and do not count) */

@@ -452,3 +452,57 @@ def test_cli_sharded_output_concatenates_to_the_unsharded_output(tmp_path):
     multi = subprocess.run(["bash", os.path.join(ROOT, "tools", "brc_multi.sh"), "3"] + args, capture_output=True, env=dict(env, BRC_NDEV="1"))
     assert multi.returncode == 0, multi.stderr.decode()[-1000:]
     assert multi.stdout == whole.stdout and len(whole.stdout.splitlines()) == 378000
+
+
+def test_cli_parallel_window_decode_yields_samfetch_records(tmp_path):
+    """Big fetches are decoded by several threads over position sub-ranges (ParallelFetcher) and concatenated: record count,
+    position sum and quality sum per region must equal the sequential reader's, whatever the thread count and window size
+    (decode-only, no device)."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import synth_cb
+    exe = _cli()
+    sp = synth_cb.Spec(seed=5, contig_len=1280 * 700)
+    info = synth_cb.write_sample_bam(sp, 0, 0, 700, str(tmp_path), REF_SAMTOOLS)
+    regions = ["chr1:1-896000", "chr1:100001-700000", "chr1:5-300", "chr1"]
+    outs = []
+    for extra in ({"BRC_CLI_SEQUENTIAL": "1"}, {}, {"BRC_CLI_DECODE_THREADS": "3"}, {"BRC_CLI_DECODE_THREADS": "16", "BRC_CLI_WINDOW": "300000"},
+                  {"BRC_CLI_SEQUENTIAL": "1", "BRC_CLI_WINDOW": "300000"}):
+        p = subprocess.run([exe, "-w", "0", info["bam"]] + regions, capture_output=True, env=dict(os.environ, BRC_CLI_DECODE_ONLY="1", BRC_CLI_TIMING="1", **extra))
+        assert p.returncode == 0, p.stderr.decode()[-1000:]
+        outs.append((p.stdout, p.stderr.decode()))
+    assert outs[0][0] == outs[1][0] == outs[2][0] and outs[3][0] == outs[4][0]
+    assert len(outs[0][0].splitlines()) == 4 and int(outs[0][0].split()[3]) > 170000
+    assert "windows decoded by" in outs[1][1] and "(+ 0 records in 0 windows" in outs[0][1] and "(+ 0 records in 0 windows" not in outs[1][1]
+
+
+@pytest.mark.gpu
+def test_cli_parallel_window_decode_text_and_warnings_equal_sequential(tmp_path):
+    """The parallel window path (one borrowed, page-locked batch per window, next window decoded ahead) against the record-by-record
+    path: STDOUT and the per-read warning lines on STDERR must be identical, also when a window boundary falls inside the region."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    from bam_readcount_b200 import synth
+    from bam_readcount_b200.batch import TAG_ABSENT
+    exe = _cli()
+    case = cases.synthetic_case(L=300000, depth=12, seed=97, regions=((0, 1, 300000),), site_list=False)
+    b = case["batch"]
+    rng = np.random.default_rng(3)
+    nm = np.array(b.nm, copy=True); nm[rng.choice(b.n_reads, 400, replace=False)] = TAG_ABSENT      # reads the reference warns about
+    import dataclasses
+    case["batch"] = dataclasses.replace(b, nm=nm)
+    d = str(tmp_path)
+    _make_bam(case, d)
+    for args in (["-w", "0", "-i"], ["-p", "-q", "20", "-b", "20"], ["-w", "7", "-p"]):
+        outs = []
+        for extra in ({"BRC_CLI_SEQUENTIAL": "1"}, {}, {"BRC_CLI_DECODE_THREADS": "3", "BRC_CLI_WINDOW": "280000"}):
+            p = subprocess.run([exe] + args + ["-f", os.path.join(d, "ref.fa"), os.path.join(d, "s.bam"), "chr1:1-300000", "chr1:1001-2000"],
+                               capture_output=True, env=dict(os.environ, **extra))
+            assert p.returncode == 0, p.stderr.decode()[-2000:]
+            outs.append((p.stdout, p.stderr))
+        assert outs[0][0] == outs[1][0] == outs[2][0] and outs[0][0].count(b"\n") > 299000
+        assert outs[0][1] == outs[1][1] == outs[2][1]
+        if args[1] != "0":
+            assert b"WARNING: In read" in outs[0][1]
