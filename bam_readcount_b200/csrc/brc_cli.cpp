@@ -864,10 +864,8 @@ int main(int argc, char **argv) {
     if (!have_fa && !decode_only) { std::fprintf(stderr, "A reference FASTA (-f) is required in region / site-list mode\n"); return 1; }
 
     cfg.n_libs = (int32_t)lib_names.size();
-    warm.join();
-    brc_engine *eng = nullptr;
-    int rc = decode_only ? BRC_OK : (warm_rc != BRC_OK ? warm_rc : brc_create(&cfg, &eng));
-    if (rc != BRC_OK) { std::fprintf(stderr, "brc_create: %s\n", brc_strerror(rc)); return 1; }
+    brc_engine *eng = nullptr;      // created below, once the first window is already being decoded (the CUDA context is still coming up)
+    int rc = BRC_OK;
 
     struct Region { int tid, beg, end; bool site_list; bool cont = false; };   // cont: a later window of a cut region (its halo site belongs to the window before)
     std::vector<Region> regions;
@@ -897,7 +895,10 @@ int main(int argc, char **argv) {
     // (the 1-site halo), so the concatenated output equals the unsplit region's.  Only the last window of an argv region keeps
     // argv semantics.  (With a tiny -d the max-count rule sees the window's own fetch order)
     {
-        int64_t W = std::getenv("BRC_CLI_WINDOW") ? std::atoll(std::getenv("BRC_CLI_WINDOW")) : 8000000;
+        // 2 Mb windows: each is decoded by all threads in ~40 ms one window ahead of the engine and needs 110 MB of page-locked memory
+        // (8 Mb windows were 0.6 s slower on a 10 Mb BAM, r02t); the record-by-record paths (CRAM, BRC_CLI_SEQUENTIAL) keep 8 Mb
+        const bool par_windows_ok = !is_cram && std::getenv("BRC_CLI_DEVICE_DECODE") == nullptr && std::getenv("BRC_CLI_SEQUENTIAL") == nullptr;
+        int64_t W = std::getenv("BRC_CLI_WINDOW") ? std::atoll(std::getenv("BRC_CLI_WINDOW")) : (par_windows_ok ? 2000000 : 8000000);
         if (shard_count > 1 && !std::getenv("BRC_CLI_WINDOW")) W = 1000000;      // finer units so the shards can balance
         std::vector<Region> cut;
         for (const Region &g : regions) {
@@ -981,11 +982,9 @@ int main(int argc, char **argv) {
         return brc_reset(eng);
     };
     int64_t pushed = 0;
-    if (eng) brc_set_queue_carry(eng, 1);    // argv regions are flushed batch by batch: their never-cleared deletion queue travels with the engine
-    const double t_loop0 = now();
     RegionFetcher fetcher(bam);
     // big fetches (windows of a cut region) are decoded by several threads, one window ahead of the engine (ParallelFetcher)
-    ParallelFetcher pf(bam, bam_path, per_lib, eng != nullptr);
+    ParallelFetcher pf(bam, bam_path, per_lib, !decode_only);
     for (const auto &kv : rg_lb) pf.rg_lib[kv.first] = lib_rank[kv.second];
     const bool allow_parallel = !is_cram && !device_decode && std::getenv("BRC_CLI_SEQUENTIAL") == nullptr;
     std::unique_ptr<WindowJob[]> jobs(new WindowJob[2]);
@@ -1021,6 +1020,12 @@ int main(int argc, char **argv) {
         par_decode_error = par_decode_error || job->error; par_decoded += job->n_decoded; ++par_windows;
         return job;
     };
+    if (!regions.empty() && par_ok(0)) { ahead_slot = 0; ahead_gi = 0; ahead = start_decode(0, 0); }   // decode under the CUDA start-up
+    warm.join();
+    rc = decode_only ? BRC_OK : (warm_rc != BRC_OK ? warm_rc : brc_create(&cfg, &eng));
+    if (rc != BRC_OK) { std::fprintf(stderr, "brc_create: %s\n", brc_strerror(rc)); return 1; }
+    if (eng) brc_set_queue_carry(eng, 1);
+    const double t_loop0 = now();
     auto next_fbeg = [&](size_t gi) -> int64_t {   // start of the following fetch when it continues this one, else "keep nothing"
         if (gi + 1 >= regions.size() || regions[gi + 1].tid != regions[gi].tid) return INT64_MAX;
         return std::max<int64_t>((int64_t)regions[gi + 1].beg - 1, 0);
@@ -1129,8 +1134,13 @@ int main(int argc, char **argv) {
                              (unsigned long long)fetcher.n_decoded, (unsigned long long)par_decoded, (unsigned long long)par_windows, pf.n_threads);
     if (decode_only) return decode_error ? 1 : 0;
     if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
-    const double t_d0 = now();
+    if (timing) std::fprintf(stderr, "[brc timing] startup (CUDA context, header, index, first window) %.3fs\n", t_loop0 - t_main0);
+    if (!std::getenv("BRC_CLI_CLEAN_EXIT")) {
+        // everything is printed: leave without tearing down the CUDA context, the page-locked buffers and the thread pools one by
+        // one (0.3-0.9 s on a B200 box, r02t) — the kernel reclaims them
+        std::fflush(nullptr);
+        _exit(decode_error ? 1 : 0);
+    }
     brc_destroy(eng);
-    if (timing) std::fprintf(stderr, "[brc timing] startup (CUDA context, header, index) %.3fs  teardown %.3fs\n", t_loop0 - t_main0, now() - t_d0);
     return decode_error ? 1 : 0;
 }

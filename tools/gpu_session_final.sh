@@ -21,6 +21,7 @@ for f in ("bench_c4","bench_ref_c4","bench_c3_full","bench_c5"):
     except Exception as ex:
         print(f, "FAILED", ex)
 PY
+[ -n "$SKIP_NCU" ] && { ls -la $O | tail -20; exit 0; }
 B="--e2e-windows 0 --no-cpu-baseline --no-e2e-text --no-parity"
 # ncu: launch list of the bench command + one full capture of K1, K0 and the deep kernel
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file $O/launches_c4.csv python bench.py --steps 1 --warmup 3 --contigs 1 $B > $O/bench_under_ncu_c4.log 2>&1
