@@ -947,7 +947,7 @@ int main(int argc, char **argv) {
     std::string chrom;
     const bool timing = std::getenv("BRC_CLI_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_decode = 0, t_compute = 0, t_format = 0, t_write = 0, t_ref = 0;
+    double t_decode = 0, t_compute = 0, t_format = 0, t_write = 0, t_ref = 0, t_results = 0, t_reset = 0;
     // BRC_CLI_DEVICE_DECODE=1: BGZF inflate + BAM framing on the GPU (per-read warning lines need host-decoded reads: counts only)
     const bool device_decode = std::getenv("BRC_CLI_DEVICE_DECODE") != nullptr && !decode_only;
     std::vector<std::string> rg_id_store; std::vector<const char *> rg_ids; std::vector<uint16_t> rg_libs;
@@ -961,9 +961,11 @@ int main(int argc, char **argv) {
         t_compute += now() - c0;
         if (r != BRC_OK) { std::fprintf(stderr, "brc_compute: %s\n", brc_last_error(eng)); return r; }
         brc_results res{};
+        const double g0 = now();
         if ((r = brc_get_results(eng, &res)) != BRC_OK) { std::fprintf(stderr, "brc_get_results: %s\n", brc_last_error(eng)); return r; }
         std::fflush(stdout);
         const double f0 = now();
+        t_results += f0 - g0;
         const bool argv_chain = res.n_regions > 1 && !res.regions[0].site_list_mode;   // never-cleared deletion queue: one sequential pass
         int64_t total_slots = 0;
         for (int64_t g = 0; g < res.n_regions; ++g) total_slots += res.regions[g].n_slots;
@@ -979,7 +981,10 @@ int main(int argc, char **argv) {
         t_format += now() - f0;
         { int64_t wc[4]; if (brc_get_warning_counts(eng, wc) == BRC_OK) for (int k = 0; k < 4; ++k) warn_total[k] += wc[k]; }
         warner.replay();
-        return brc_reset(eng);
+        const double r0 = now();
+        const int rr = brc_reset(eng);
+        t_reset += now() - r0;
+        return rr;
     };
     int64_t pushed = 0;
     RegionFetcher fetcher(bam);
@@ -1133,7 +1138,8 @@ int main(int argc, char **argv) {
     if (timing) std::fprintf(stderr, "[brc timing] index seeks %llu  records decoded %llu  (+ %llu records in %llu windows decoded by %d threads)\n", (unsigned long long)fetcher.n_seeks,
                              (unsigned long long)fetcher.n_decoded, (unsigned long long)par_decoded, (unsigned long long)par_windows, pf.n_threads);
     if (decode_only) return decode_error ? 1 : 0;
-    if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  format %.3fs  write %.3fs\n", t_ref, t_decode, t_compute, t_format, t_write);
+    if (timing) std::fprintf(stderr, "[brc timing] reference %.3fs  decode+push %.3fs  compute %.3fs  results %.3fs  format %.3fs  reset %.3fs  write %.3fs  | region loop %.3fs, since main() %.3fs\n",
+                             t_ref, t_decode, t_compute, t_results, t_format, t_reset, t_write, now() - t_loop0, now() - t_main0);
     if (timing) std::fprintf(stderr, "[brc timing] startup (CUDA context, header, index, first window) %.3fs\n", t_loop0 - t_main0);
     if (!std::getenv("BRC_CLI_CLEAN_EXIT")) {
         // everything is printed: leave without tearing down the CUDA context, the page-locked buffers and the thread pools one by
