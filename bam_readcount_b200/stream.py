@@ -3,13 +3,15 @@
 The reference's unit of independence is the region: a fresh pileup buffer per region (R:…:591, :650), the deletion queue
 cleared per site-list line (R:…:605).  A genome is therefore cut into WINDOWS (regions of a few Mb — what fits HBM next to its
 results), windows are dealt to ranks as contiguous SHARDS balanced by a coverage weight (the BAI linear index for a real BAM,
-uniform for the synthetic genome), and every rank walks its shard double-buffered on two engine handles: while window w runs
-on one handle's stream, window w+1's reads are produced (generator / H2D) and planned on the other.  Window [b, e) computes
+uniform for the synthetic genome), and every rank walks its shard on three engine handles: while window w runs on one handle's
+stream, the next windows' reads are produced (generator / already resident in HBM) and planned on the others.  Window [b, e) computes
 site b-1 as its halo (R:…:269 vs :414), so no state crosses a window or a rank.
 
 The only inter-rank traffic is the ORDERED EMIT: every rank sends the packed records of each finished window to rank 0
-(`GatherRing`: ncclSend/ncclRecv through torch.distributed P2P ops inside one group per round, after an all-gather of
-the variable record counts); ranks hold ascending site ranges, so rank 0 spools shard by shard in rank order.
+(`GatherRing`: ncclSend/ncclRecv through torch.distributed P2P ops inside one group per round; `round_fixed` sends
+messages whose sizes follow from the shard plan, queued behind the kernels with no host synchronisation; `round` is the
+variable-size form with an all-gather of the byte counts first); ranks hold ascending site ranges, so rank 0 spools shard by
+shard in rank order, into two spool sets per source, and consumes them on an emitter stream of its own.
 """
 from __future__ import annotations
 
@@ -182,10 +184,11 @@ class WindowRunner:
 class GatherRing:
     """Ordered-emit transport: rank 0 receives every other rank's packed window records over the process group.
 
-    One ROUND = the k-th window of every rank.  Protocol per round: all-gather of (words bytes, sec bytes) per rank,
-    then ONE group of point-to-point ops (NCCL: ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd) — two sends on
-    every rank > 0, 2 x (N-1) receives on rank 0 into per-source spool buffers.  `consume(src, words, sec)` is called
-    on rank 0 for every received pair (the emitter; bench.py checksums the bytes)."""
+    One ROUND = the k-th window of every rank: ONE group of point-to-point ops (NCCL: ncclGroupStart / ncclSend / ncclRecv /
+    ncclGroupEnd) — the sends of every rank > 0, the matching receives on rank 0 into that round's per-source spool buffers (two
+    sets, alternating).  `round_fixed`: message sizes known from the shard plan (words, a bounded pool message, the 4-byte true
+    count), nothing waits on the host.  `round`: an all-gather of (words bytes, pool bytes) first, then exact sizes.
+    `consume(src, words, sec)` is called on rank 0 for every received pair on the emitter stream (bench.py checksums the bytes)."""
 
     def __init__(self, rank: int, world: int, device, max_words_bytes: int, max_sec_bytes: int, group=None, consume=None):
         import torch
