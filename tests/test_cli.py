@@ -506,3 +506,50 @@ def test_cli_parallel_window_decode_text_and_warnings_equal_sequential(tmp_path)
         assert outs[0][1] == outs[1][1] == outs[2][1]
         if args[1] != "0":
             assert b"WARNING: In read" in outs[0][1]
+
+
+def test_cli_parallel_window_decode_two_contigs_unmapped_and_edges(tmp_path):
+    """CPU: the parallel window decode on a two-contig BAM with placed-but-unmapped records, a fetch that starts inside a read,
+    a fetch past the last read, a site-list line long enough to be cut into windows, and a contig without reads behind it:
+    per-region (count, position sum, quality sum) identical to the sequential reader and to the Python decoder's samfetch."""
+    from oracle.oracle import REF_SAMTOOLS
+    if not os.path.exists(REF_SAMTOOLS):
+        pytest.skip("oracle/_ref/samtools not built")
+    import dataclasses
+    from bam_readcount_b200 import synth
+    from bam_readcount_b200.batch import ReadBatch
+    exe = _cli()
+    a = cases.synthetic_case(L=600000, depth=4, seed=31, regions=((0, 1, 600000),), site_list=False)["batch"]
+    b = cases.synthetic_case(L=400000, depth=5, seed=32, regions=((0, 1, 400000),), site_list=False)["batch"]
+    rng = np.random.default_rng(9)
+    fa = np.array(a.flag, copy=True); fa[rng.choice(a.n_reads, 300, replace=False)] |= 4          # unmapped but placed (mate-anchored)
+    a = dataclasses.replace(a, flag=fa)
+    b = dataclasses.replace(b, tid=np.ones_like(b.tid))
+    both = ReadBatch.concat([a, b])
+    d = str(tmp_path)
+    synth.write_sam(os.path.join(d, "s.sam"), both, [("chrA", 600000), ("chrB", 400000), ("chrC", 300000)])
+    subprocess.check_call([REF_SAMTOOLS, "view", "-b", "-o", os.path.join(d, "s.bam"), os.path.join(d, "s.sam")])
+    subprocess.check_call([REF_SAMTOOLS, "index", os.path.join(d, "s.bam")])
+    lines = [("chrA", 1, 600000), ("chrA", 100077, 500000), ("chrB", 50, 399000), ("chrA", 300000, 300001), ("chrB", 120000, 400000),
+             ("chrC", 1, 300000), ("chrA", 590000, 600000)]
+    sl = tmp_path / "sites"
+    sl.write_text("".join(f"{c}\t{s}\t{e}\n" for c, s, e in lines))
+    outs = []
+    for extra in ({"BRC_CLI_SEQUENTIAL": "1"}, {}, {"BRC_CLI_DECODE_THREADS": "5", "BRC_CLI_WINDOW": "270000"}, {"BRC_CLI_SEQUENTIAL": "1", "BRC_CLI_WINDOW": "270000"}):
+        p = subprocess.run([exe, "-l", str(sl), os.path.join(d, "s.bam")], capture_output=True, env=dict(os.environ, BRC_CLI_DECODE_ONLY="1", BRC_CLI_TIMING="1", **extra))
+        assert p.returncode == 0, p.stderr.decode()[-1500:]
+        outs.append((p.stdout.decode(), p.stderr.decode()))
+    assert outs[0][0] == outs[1][0] and outs[2][0] == outs[3][0]
+    assert "(+ 0 records in 0 windows" not in outs[1][1] and "(+ 0 records in 0 windows" not in outs[2][1]
+    got = [tuple(int(x) for x in ln.split("\t")) for ln in outs[0][0].strip().splitlines()]
+    assert len(got) == len(lines)
+    qo = both.qual_off.astype(np.int64)
+    mapped = (both.flag & 4) == 0
+    for (c, s, e), g in zip(lines, got):
+        tid = {"chrA": 0, "chrB": 1, "chrC": 2}[c]
+        idx = [i for i in both.fetch(tid, max(s - 2, 0), e) if mapped[i]]
+        want = (tid, s - 1, e, len(idx), int(both.pos[idx].astype(np.int64).sum()) if idx else 0, int(sum(int(both.qual[qo[i]:qo[i + 1]].astype(np.int64).sum()) for i in idx)))
+        assert g == want, (c, s, e, g, want)
+    # the cut form prints one line per window: their sums are the uncut line's
+    cut = [tuple(int(x) for x in ln.split("\t")) for ln in outs[2][0].strip().splitlines()]
+    assert len(cut) > len(lines)
