@@ -147,7 +147,7 @@ def _gather_worker(rank, world, port, q):
         ring.round(tw, ts)
     # the size-exchange-free protocol (fixed message sizes known from the shard plan): words, pool bound, 4-byte count
     fixed_sent = []
-    for k in range(2):
+    for k in range(5):                                   # five rounds: both spool sets of rank 0 are reused
         nw, ns = 64 * (k + 1), 144
         mine = None
         if rank == 1:
@@ -178,7 +178,7 @@ def test_gather_ring_two_ranks_gloo():
         assert p.exitcode == 0
     got0, _ = res[0]
     _, sent1 = res[1]
-    assert [g[0] for g in got0] == [1, 1, 1, 1, 1]
+    assert [g[0] for g in got0] == [1] * 8                 # three variable-size rounds + five fixed-size rounds
     assert [(g[1], g[2]) for g in got0] == sent1          # rank 0 received rank 1's records, round by round, byte for byte
     assert res[1][0] == []
 
